@@ -1,0 +1,219 @@
+/*
+ * pdlp_b200.h -- C ABI of the B200-native restarted-PDHG LP engine.
+ *
+ * This is the drop-in boundary for torchPDLP's hot path.  torchPDLP has no
+ * FFI / plugin registry of its own: its boundary is the
+ * Python call surface of PDLP/primal_dual_hybrid_gradient.py,
+ * PDLP/primal_dual_hybrid_gradient_step.py, PDLP/helpers.py and
+ * PDLP/enhancements.py.  Each entry point below names the reference function
+ * (file:line under /root/reference) whose device work it replaces; the ctypes
+ * binding a torchPDLP maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Every function returns 0 on success and a nonzero pdlp_status on error;
+ *     pdlp_last_error() returns a thread-local message.  Nothing throws.
+ *   - All vector / matrix pointers are DEVICE pointers (cudaMalloc'ed or
+ *     tensor.data_ptr()) unless the parameter name starts with `host_`.
+ *   - Values are fp64 (PDLP_F64) or fp32 (PDLP_F32); indices are int32.
+ *   - Work is enqueued on the `stream` given at pdlp_create (pass torch's
+ *     current stream).  Functions that return scalars to the host synchronise
+ *     that stream; the others are asynchronous.
+ *   - A handle is bound to the CUDA device current at pdlp_create and is not
+ *     thread-safe.  The library copies the problem data into its own buffers
+ *     (so Ruiz scaling never mutates caller memory) and owns its workspace.
+ *   - There is no CPU fallback: with no CUDA device every call fails with
+ *     PDLP_ERR_CUDA.
+ */
+#ifndef PDLP_B200_H_
+#define PDLP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdlp_engine* pdlp_handle;
+
+enum pdlp_dtype { PDLP_F64 = 0, PDLP_F32 = 1 };
+
+enum pdlp_status {
+  PDLP_OK = 0,
+  PDLP_ERR_INVALID = 1, /* bad argument */
+  PDLP_ERR_CUDA = 2,    /* CUDA runtime error (message has the cudaError string) */
+  PDLP_ERR_STATE = 3    /* call sequence error (e.g. restart check before any iteration) */
+};
+
+/* Restart kinds reported by pdlp_restart_check (reference
+ * primal_dual_hybrid_gradient.py:131-141). */
+enum pdlp_restart_kind {
+  PDLP_RESTART_NONE = 0,
+  PDLP_RESTART_SUFFICIENT = 1,
+  PDLP_RESTART_NECESSARY = 2,
+  PDLP_RESTART_ARTIFICIAL = 3,
+  PDLP_RESTART_FORCED = 4 /* inner loop left because the KKT-pass limit was hit (:67) */
+};
+
+/* Infeasibility verdicts (reference enhancements.py:141,159). */
+enum pdlp_infeas { PDLP_FEASIBLE_SO_FAR = 0, PDLP_DUAL_INFEASIBLE = 1, PDLP_PRIMAL_INFEASIBLE = 2 };
+
+/* Residuals of one iterate: helpers.py:53-96 (compute_residuals_and_duality_gap)
+ * plus helpers.py:98-108 (KKT_error).  pr_unscaled / dr_unscaled are the same
+ * norms taken on the un-preconditioned problem (reference :157-163); they equal
+ * pr / dr when no scaling is active. */
+typedef struct pdlp_residuals {
+  double pr;          /* ||[ (Kx-q)_eq ; min((Kx-q)_ineq, 0) ]||_2 */
+  double dr;          /* ||g - lambda||_2,  g = c - K^T y */
+  double gap;         /* adjusted_dual - prim_obj, signed */
+  double prim_obj;    /* c^T x */
+  double adj_dual;    /* q^T y + l_dual^T max(lambda,0) + u_dual^T min(lambda,0) */
+  double kkt;         /* sqrt(w^2 pr^2 + dr^2 / w^2 + gap^2) at the omega in force */
+  double pr_unscaled;
+  double dr_unscaled;
+} pdlp_residuals;
+
+/* Host-visible snapshot of the solver scalars (all kept on the device between
+ * calls; this is a copy). */
+typedef struct pdlp_state {
+  double eta;         /* step size the NEXT iteration will use */
+  double omega;       /* primal weight */
+  double theta;       /* extrapolation (reference always passes 1.0) */
+  double eta_sum;     /* sum of averaging weights since the last restart */
+  double last_weight; /* averaging weight of the latest iterate (step.py:110-115) */
+  double dx2, dy2, inter; /* ||dx||^2, ||dy||^2, dy^T K dx of the latest step */
+  double kkt_first;   /* KKT error at the last restart point */
+  double q_norm, c_norm;
+  int64_t k;          /* total iterations */
+  int32_t t;          /* iterations since the last restart */
+  int32_t n_restarts;
+  int32_t infeas;     /* pdlp_infeas */
+  int32_t infeas_k;   /* iteration at which it was detected */
+  int32_t solved;     /* 1 when the last restart point met check_termination */
+  int32_t reserved;
+} pdlp_state;
+
+/* Result of one restart check. */
+typedef struct pdlp_check {
+  int32_t kind;        /* pdlp_restart_kind; NONE = keep iterating */
+  int32_t use_average; /* 1: restart point is the weighted average (ties -> average, :133) */
+  int32_t t;           /* inner iteration count at the check */
+  int32_t solved;      /* check_termination (helpers.py:110-128) on the restart point */
+  int64_t k;
+  double omega;        /* after primal_weight_update when enabled (enhancements.py:73-78) */
+  double kkt_current, kkt_average, kkt_previous, kkt_first_new;
+  pdlp_residuals point; /* residuals of the chosen restart point (what the reference prints, :167-170) */
+} pdlp_check;
+
+const char* pdlp_last_error(void);
+
+/* Number of bytes the engine believes one PDHG iteration must move
+ * (SURVEY.md section 8d).  For reporting only. */
+int64_t pdlp_bytes_per_iteration(pdlp_handle h);
+
+/* ---- lifetime -------------------------------------------------------------
+ * Problem tuple (c, K, q, m_ineq, l, u): reference PDLP/util.py:239-269,
+ * consumed at primal_dual_hybrid_gradient.py:7.  K is given as CSR (m x n) AND
+ * as CSR of K^T (n x m) with column indices sorted inside each row, so both
+ * products are row-parallel and atomic-free.  l/u may hold -inf/+inf.        */
+int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
+                const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals,
+                const void* c, const void* q, const void* l, const void* u, void* stream);
+int pdlp_destroy(pdlp_handle h);
+
+/* ---- iterate / scalars ----------------------------------------------------
+ * x_init / y_init of pdlp_algorithm (:31-36).  Also resets the averaging sums,
+ * t and the restart snapshot (:58-64).                                        */
+int pdlp_set_iterate(pdlp_handle h, const void* x, const void* y);
+int pdlp_get_iterate(pdlp_handle h, void* x, void* y);
+/* Weighted-average iterate of the current epoch (:118-119). */
+int pdlp_get_average(pdlp_handle h, void* x_avg, void* y_avg);
+/* eta, omega, theta as at :22-25; adaptive selects step.py:43-115 vs :3-40. */
+int pdlp_set_step(pdlp_handle h, double eta, double omega, double theta, int adaptive);
+/* tol (:7), primal_update (:150-151), infeasibility detection (:89-101). */
+int pdlp_set_options(pdlp_handle h, double tol, int primal_update, int infeasibility_detect, double infeas_tol);
+int pdlp_get_state(pdlp_handle h, pdlp_state* host_out);
+/* Iteration counters k (total, :76) and t (since restart, :104): the adaptive rule
+ * reads k (step.py:102,107), the artificial restart test reads both (:139). */
+int pdlp_set_counters(pdlp_handle h, int64_t k, int32_t t);
+
+/* ---- the hot loop -----------------------------------------------------------
+ * n_iters PDHG iterations (fixed_one_step_pdhg step.py:3-40 or
+ * adaptive_one_step_pdhg step.py:43-115, plus the averaging update :104-112),
+ * two kernels per iteration, scalars stay on the device.  With
+ * save_previous != 0 the iterate before the LAST step is kept for the restart
+ * test (:77-78,:126).  use_graph != 0 replays a cached CUDA graph.  Async.    */
+int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int use_graph);
+
+/* Restart test + restart epilogue (:115-177): averages, the three KKT errors
+ * with ONE pass over K and one over K^T, the sufficient / necessary / artificial
+ * criteria, candidate selection, primal-weight update, KKT_first, termination
+ * test.  force != 0 evaluates and restarts at the current iterate (loop left by
+ * the KKT-pass limit, :67 then :148).  Synchronises; fills *host_out.         */
+int pdlp_restart_check(pdlp_handle h, int force, pdlp_check* host_out);
+
+/* helpers.py:53-108 for caller-supplied vectors (x: n, y: m) at primal weight
+ * omega.  Synchronises. */
+int pdlp_kkt(pdlp_handle h, const void* x, const void* y, double omega, pdlp_residuals* host_out);
+
+/* c^T x of the current iterate (what pdlp_algorithm returns as prim_obj when an
+ * infeasibility certificate ends the solve, :95).  Synchronises. */
+int pdlp_primal_objective(pdlp_handle h, double* host_out);
+
+/* ---- setup-time kernels -----------------------------------------------------
+ * Power iteration spectral_norm_estimate_torch (helpers.py:41-51) started from
+ * b0 (n values, the caller draws it: reference uses torch.randn).  Synchronises. */
+int pdlp_power_iteration(pdlp_handle h, const void* b0, int iters, double* host_sigma);
+/* out = K in (transpose == 0, in: n, out: m) or K^T in (transpose != 0). Async. */
+int pdlp_spmv(pdlp_handle h, int transpose, const void* in, void* out);
+/* Ruiz equilibration, ruiz_precondition (enhancements.py:43-71), in place on the
+ * engine's copy of (K, K^T, c, q, l, u).  Synchronises; *host_rounds = rounds run. */
+int pdlp_ruiz(pdlp_handle h, int max_iter, double eps, int* host_rounds);
+/* Pock-Chambolle (alpha = 1) on top of the current scaling.  No reference
+ * implementation exists in the snapshot (main.py:8 imports a missing symbol). */
+int pdlp_pock_chambolle(pdlp_handle h);
+/* D_row (m), D_col (n): accumulated scalings, ones when none was applied. */
+int pdlp_get_scaling(pdlp_handle h, void* D_row, void* D_col);
+/* Declare that the problem held by the engine is ALREADY scaled by (D_row, D_col)
+ * (data_precond of pdlp_algorithm, :157-163): termination residuals are then taken
+ * on the unscaled problem.  Does not touch the data. */
+int pdlp_set_scaling(pdlp_handle h, const void* D_row, const void* D_col);
+/* Current (possibly scaled) problem vectors; any pointer may be NULL. */
+int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u);
+/* Current (possibly scaled) values of K in the caller's CSR order (nnz values). */
+int pdlp_get_matrix_values(pdlp_handle h, void* K_vals);
+
+/* ---- whole solve --------------------------------------------------------------
+ * pdlp_algorithm (primal_dual_hybrid_gradient.py:7-181) driven from C++:
+ * restart loop, counters k / n / j with the reference's accounting, KKT-pass and
+ * wall-clock limits.  The step size / primal weight / iterate must have been
+ * set (pdlp_set_step, pdlp_set_iterate).                                       */
+typedef struct pdlp_solve_options {
+  int64_t max_kkt;       /* :7  default 100000 */
+  int32_t restart_period;/* main.py:132 passes 40 */
+  int32_t use_graph;
+  double time_limit;     /* seconds, :68-74 */
+  double time_used;      /* seconds already spent by the caller (:69) */
+  int32_t max_trace;     /* capacity of host_trace (records), 0 = none */
+  int32_t reserved;
+} pdlp_solve_options;
+
+typedef struct pdlp_solve_result {
+  int64_t k, j;
+  int32_t n;
+  int32_t status;        /* 0 Solved, 1 KKT-pass limit, 2 time limit, 3 PRIMAL_INFEASIBLE, 4 DUAL_INFEASIBLE */
+  double prim_obj;
+  double seconds;        /* wall clock inside pdlp_solve + time_used */
+  double device_ms;      /* CUDA-event time of the whole loop */
+  int32_t n_trace;       /* records written to host_trace */
+  int32_t reserved;
+} pdlp_solve_result;
+
+int pdlp_solve(pdlp_handle h, const pdlp_solve_options* opts, pdlp_solve_result* host_out,
+               pdlp_check* host_trace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDLP_B200_H_ */

@@ -1,0 +1,180 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden vectors produced by executing
+the reference, host-side logic, and the C-ABI library's exported symbols."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdlp_oracle as orc
+from torchpdlp_b200 import synthetic
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLD, "cfg1_reference.json")) as f:
+        return json.load(f)
+
+
+def test_generator_is_the_fixture_lp(cfg1, gold):
+    assert (cfg1.m, cfg1.n, cfg1.nnz, cfg1.m_ineq) == (gold["lp"]["m"], gold["lp"]["n"], gold["lp"]["nnz"],
+                                                       gold["lp"]["m_ineq"])
+    assert cfg1.bytes_per_iteration() == 24 * 20000 + 4 * 3002 + 72 * 2000 + 48 * 1000
+
+
+def run_oracle(lp, o, layout="csr", backend="torch"):
+    torch.set_default_dtype(torch.float64)
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout=layout)
+    torch.manual_seed(0)
+    op = orc.Operator(K, backend=backend)
+    c, q, l, u = (v.reshape(-1) for v in (c, q, l, u))
+    kw = {}
+    if o["ruiz"]:
+        sop, cs, qs, ls, us, sc = orc.precondition(op, c, q, l, u)
+        kw = dict(scaling=sc, unscaled=(op, c, q, l, u))
+        op, c, q, l, u = sop, cs, qs, ls, us
+    x0 = y0 = None
+    if o["fishnet"]:
+        x0, y0 = orc.spectral_cast(op, c, q, l, u, m_ineq, k=32)
+    return orc.pdlp_algorithm(op, m_ineq, c, q, l, u, primal_update=o["primal_weight"], adaptive=o["adaptive"],
+                              x_init=x0, y_init=y0, **kw)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 8, 11, 6])
+def test_oracle_reproduces_executed_reference(idx, cfg1, gold):
+    """Dense K, the layout the reference ran: k / n / j / status / restart kinds equal,
+    objective to 1e-9 (fixed step) or 2e-6 (adaptive: chaotic in the last bit)."""
+    run = gold["runs"][idx]
+    o, ref = run["options"], run["reference"]
+    sol = run_oracle(cfg1, o, layout="dense")
+    assert (sol.k, sol.n, sol.j, sol.status) == (ref["k"], ref["n"], ref["j"], ref["status"])
+    assert [(r.kind, str(r.t), r.candidate) for r in sol.trace] == [tuple(r) for r in ref["restarts"]]
+    assert rel(sol.prim_obj, ref["obj"]) < (2e-6 if o["adaptive"] else 1e-9)
+
+
+def test_oracle_sparse_backends_agree(cfg1, gold):
+    ref = gold["runs"][0]["reference"]
+    for layout, backend in [("coo", "torch"), ("csr", "torch"), ("csr", "scipy")]:
+        sol = run_oracle(cfg1, gold["runs"][0]["options"], layout=layout, backend=backend)
+        assert (sol.k, sol.n, sol.j, sol.status) == (ref["k"], ref["n"], ref["j"], ref["status"])
+        assert rel(sol.prim_obj, ref["obj"]) < 1e-9
+
+
+def test_oracle_function_pins(cfg1):
+    """Single calls of step / residual / KKT / power iteration / Ruiz against outputs
+    saved from the executed reference (cfg1_functions.npz)."""
+    torch.set_default_dtype(torch.float64)
+    z = np.load(os.path.join(GOLD, "cfg1_functions.npz"))
+    c, K, q, m_ineq, l, u = cfg1.torch_tensors(layout="dense")
+    op = orc.Operator(K)
+    v = lambda t: t.reshape(-1)
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    eta, omega = float(z["eta"]), float(z["omega"])
+    fx, fy = orc.fixed_one_step_pdhg(x, y, v(c), v(q), op, v(l), v(u), m_ineq, eta, omega)
+    np.testing.assert_allclose(fx.numpy(), z["fixed_x"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(fy.numpy(), z["fixed_y"], rtol=0, atol=1e-12)
+    ax, ay, aw, an = orc.adaptive_one_step_pdhg(x, y, v(c), v(q), op, v(l), v(u), m_ineq, eta, omega, 1.0,
+                                                int(z["adaptive_k"]))
+    np.testing.assert_allclose(ax.numpy(), z["adaptive_x"], rtol=0, atol=1e-13)
+    assert rel(aw, float(z["adaptive_w"])) < 1e-12 and rel(an, float(z["adaptive_next"])) < 1e-12
+    lo, up = torch.isinf(v(l)) & (v(l) < 0), torch.isinf(v(u)) & (v(u) > 0)
+    r = orc.compute_residuals_and_duality_gap(x, y, v(c), v(q), op, m_ineq, lo, up, v(l), v(u))
+    for a, b in zip((r.pr, r.dr, r.gap, r.prim_obj, r.adj_dual), z["residuals"]):
+        assert rel(a, float(b)) < 1e-12
+    assert rel(r.kkt(omega), float(z["kkt"])) < 1e-12
+    torch.manual_seed(5)
+    assert rel(float(orc.spectral_norm_estimate(op, 100)), float(z["sigma"])) < 1e-12
+    sop, cs, qs, ls, us, sc = orc.precondition(op, v(c), v(q), v(l), v(u))
+    np.testing.assert_allclose(sc.D_col.numpy(), z["ruiz_D_col"], rtol=1e-13)
+    np.testing.assert_allclose(sc.D_row.numpy(), z["ruiz_D_row"], rtol=1e-13)
+    np.testing.assert_allclose(sop.K.sum(dim=1).numpy(), z["ruiz_K_rowsum"], rtol=1e-11, atol=1e-13)
+    assert sc.rounds == 19
+
+
+def test_oracle_infeasibility_statuses(gold):
+    """The reference's (unreliable) certificate heuristic is matched verdict for verdict,
+    including the LPs it mislabels."""
+    torch.set_default_dtype(torch.float64)
+    cases = {"primal_infeasible": synthetic.infeasible_lp(40, 10, 100, 10, seed=0),
+             "dual_infeasible": synthetic.unbounded_lp(seed=0),
+             "feasible": synthetic.uniform_rows_lp(40, 10, 100, 10, seed=0, name="small")}
+    for rec in gold["infeasibility"]:
+        if rec["adaptive"] and rec["status"].startswith("Unsolved"):
+            continue   # 20k-pass runs: covered by make_golden.py, too slow for the CPU suite
+        lp = cases[rec["case"]]
+        c, K, q, m_ineq, l, u = lp.torch_tensors(layout="dense")
+        torch.manual_seed(0)
+        sol = orc.pdlp_algorithm(K, m_ineq, c, q, l, u, adaptive=rec["adaptive"], infeasibility_detect=True,
+                                 max_kkt=20000)
+        assert (sol.k, sol.n, sol.j, sol.status) == (rec["k"], rec["n"], rec["j"], rec["status"])
+        assert rel(sol.prim_obj, rec["obj"]) < 1e-8
+
+
+def test_oracle_optimum_close_to_highs(cfg1):
+    """Independent ground truth (HiGHS, recorded in BASELINE.md): -4273.261910622."""
+    sol = run_oracle(cfg1, dict(ruiz=False, fishnet=False, adaptive=True, primal_weight=False))
+    assert rel(sol.prim_obj, -4273.261910622) < 2e-5
+
+
+def test_oracle_edge_cases():
+    torch.set_default_dtype(torch.float64)
+    # no inequality rows, free and half-bounded variables, an empty row and an empty column
+    K = torch.tensor([[1.0, 1.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [1.0, -1.0, 0.0, 1.0]])
+    c = torch.tensor([1.0, 2.0, 0.0, 0.5]); q = torch.tensor([1.0, 0.0, 0.2])
+    l = torch.tensor([0.0, -float("inf"), -float("inf"), 0.0]); u = torch.tensor([float("inf"), 3.0, float("inf"), 2.0])
+    torch.manual_seed(0)
+    sol = orc.pdlp_algorithm(K, 0, c, q, l, u, adaptive=True, tol=1e-8, max_kkt=50_000)
+    assert sol.status == "Solved"
+    # optimum: min x0 + 2 x1 + .5 x3, x0 + x1 = 1, x0 - x1 + x3 = .2 -> x = (0.6, 0.4, *, 0): 1.4; or x3>0: check by LP
+    from scipy.optimize import linprog
+    ref = linprog(c.numpy(), A_eq=K.numpy()[[0, 2]], b_eq=q.numpy()[[0, 2]],
+                  bounds=[(0, None), (None, 3), (None, None), (0, 2)], method="highs")
+    assert abs(sol.prim_obj - ref.fun) < 1e-5
+    lam = orc.project_lambda_box(torch.tensor([-1.0, 2.0, 3.0, -4.0]), torch.isinf(l) & (l < 0), torch.isinf(u) & (u > 0))
+    assert lam.tolist() == [0.0, 0.0, 0.0, -4.0]
+
+
+# ---------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    """include/pdlp_b200.h <-> libpdlp_b200.so <-> the ctypes table, without touching a GPU."""
+    from torchpdlp_b200 import _lib
+    _lib.build()
+    with open(os.path.join(ROOT, "include", "pdlp_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(pdlp_[a-z_0-9]+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    lib = _lib.lib()
+    assert lib.pdlp_last_error() is not None
+    assert lib.pdlp_destroy(None) == 0
+    assert lib.pdlp_bytes_per_iteration(None) == 0
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from torchpdlp_b200.engine import Engine
+    lp = synthetic.feasible_lp(50, 20, 5, 0.2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u)
+
+
+def test_product_never_imports_oracle():
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "torchpdlp_b200", "**", "*.py"), recursive=True):
+        with open(path) as f:
+            src = f.read()
+        assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "") or "import" not in \
+            "".join(l for l in src.splitlines() if "oracle" in l and not l.strip().startswith("#")), path

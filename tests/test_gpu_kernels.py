@@ -1,0 +1,186 @@
+"""-m gpu: every kernel behind the C ABI against the oracle on the same seeded inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import pdlp_oracle as orc
+from torchpdlp_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(lp, dtype=torch.float64):
+    from torchpdlp_b200.engine import Engine
+    return Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u, dtype=dtype)
+
+
+def oracle_parts(lp):
+    op = orc.Operator(lp.K, backend="scipy")
+    t = lambda v: torch.from_numpy(np.asarray(v, dtype=np.float64))
+    return op, t(lp.c), t(lp.q), t(lp.l), t(lp.u)
+
+
+def ragged_lp(seed=3):
+    """Rows of every kind in one matrix: empty rows, 1-entry rows, a 5000-entry row
+    (longer than one shared-memory stage -> the long-row path), dense-ish blocks."""
+    rng = np.random.default_rng(seed)
+    m, n = 700, 6000
+    lens = rng.integers(0, 40, size=m)
+    lens[::17] = 0
+    lens[5] = 5000
+    lens[300] = 2300
+    lens[699] = 1
+    rows = np.repeat(np.arange(m), lens)
+    cols = np.concatenate([np.sort(rng.choice(n, size=L, replace=False)) for L in lens]) if lens.sum() else np.array([])
+    vals = rng.normal(size=rows.size)
+    K = sp.csr_matrix((vals, (rows, cols)), shape=(m, n))
+    K.sort_indices()
+    K = sp.csr_matrix((K.data, K.indices.astype(np.int32), K.indptr.astype(np.int32)), shape=K.shape)
+    l = rng.uniform(-5, 0, size=n)
+    u = l + rng.uniform(0.5, 5, size=n)
+    l[::7] = -np.inf
+    u[::5] = np.inf
+    return synthetic.SyntheticLP("ragged", K, rng.normal(size=n), rng.normal(size=m), l, u, 400)
+
+
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_spmv_both_directions(which, cfg1):
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    eng = make_engine(lp)
+    rng = np.random.default_rng(0)
+    v, w = rng.normal(size=lp.n), rng.normal(size=lp.m)
+    got = eng.spmv(v).cpu().numpy()
+    ref = lp.K @ v
+    assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    got_t = eng.spmv(w, transpose=True).cpu().numpy()
+    ref_t = lp.K.T @ w
+    assert np.max(np.abs(got_t - ref_t)) <= 1e-12 * max(1.0, np.max(np.abs(ref_t)))
+    eng.close()
+
+
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_fixed_and_adaptive_step_match_oracle(which, cfg1):
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    op, c, q, l, u = oracle_parts(lp)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(lp.n, generator=g, dtype=torch.float64) * 2 - 1
+    y = torch.randn(lp.m, generator=g, dtype=torch.float64)
+    y[:lp.m_ineq] = y[:lp.m_ineq].abs()
+    eta, omega = 0.07, 1.3
+    eng = make_engine(lp)
+    # fixed step (step.py:22-40)
+    ox, oy = orc.fixed_one_step_pdhg(x, y, c, q, op, l, u, lp.m_ineq, eta, omega)
+    eng.set_iterate(x, y)
+    eng.set_step(eta, omega, 1.0, adaptive=False)
+    eng.iterate(1, use_graph=False)
+    gx, gy = (t.cpu() for t in eng.get_iterate())
+    assert torch.max(torch.abs(gx - ox)) <= 1e-12 * max(1.0, float(ox.abs().max()))
+    assert torch.max(torch.abs(gy - oy)) <= 1e-12 * max(1.0, float(oy.abs().max()))
+    st = eng.state()
+    assert st.k == 1 and st.t == 1 and st.last_weight == eta and st.eta == eta
+    # adaptive step (step.py:64-115), several k so both branches of the rule are hit
+    for k, eta_k in [(1, 0.07), (7, 5.0), (400, 1e-3)]:
+        ox, oy, ow, on = orc.adaptive_one_step_pdhg(x, y, c, q, op, l, u, lp.m_ineq, eta_k, omega, 1.0, k)
+        eng.set_iterate(x, y)
+        eng.set_step(eta_k, omega, 1.0, adaptive=True)
+        eng.set_counters(k - 1, 0)
+        eng.iterate(1, use_graph=False)
+        gx, gy = (t.cpu() for t in eng.get_iterate())
+        st = eng.state()
+        assert torch.max(torch.abs(gx - ox)) <= 1e-12 * max(1.0, float(ox.abs().max()))
+        assert torch.max(torch.abs(gy - oy)) <= 1e-11 * max(1.0, float(oy.abs().max()))
+        assert abs(st.last_weight - ow) <= 1e-9 * abs(ow), (k, st.last_weight, ow)
+        assert abs(st.eta - on) <= 1e-9 * abs(on), (k, st.eta, on)
+        assert st.k == k
+    eng.close()
+
+
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_kkt_matches_oracle(which, cfg1):
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    op, c, q, l, u = oracle_parts(lp)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(lp.n, generator=g, dtype=torch.float64)
+    y = torch.randn(lp.m, generator=g, dtype=torch.float64)
+    lo, up = torch.isinf(l) & (l < 0), torch.isinf(u) & (u > 0)
+    ld, ud = torch.where(lo, torch.zeros_like(l), l), torch.where(up, torch.zeros_like(u), u)
+    ref = orc.compute_residuals_and_duality_gap(x, y, c, q, op, lp.m_ineq, lo, up, ld, ud)
+    eng = make_engine(lp)
+    got = eng.kkt(x, y, 0.8)
+    for name, a, b in [("pr", got.pr, ref.pr), ("dr", got.dr, ref.dr), ("gap", got.gap, ref.gap),
+                       ("prim_obj", got.prim_obj, ref.prim_obj), ("adj_dual", got.adj_dual, ref.adj_dual),
+                       ("kkt", got.kkt, ref.kkt(0.8))]:
+        assert abs(a - b) <= 1e-11 * max(1.0, abs(b)), (name, a, b)
+    eng.close()
+
+
+def test_power_iteration_matches_oracle(cfg1):
+    op, *_ = oracle_parts(cfg1)
+    torch.manual_seed(5)
+    b0 = torch.randn(cfg1.n, 1, dtype=torch.float64)
+    ref = float(orc.spectral_norm_estimate(op, 100, b0=b0))
+    eng = make_engine(cfg1)
+    got = eng.power_iteration(b0, 100)
+    assert abs(got - ref) <= 1e-10 * ref
+    npz = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_functions.npz"))
+    assert abs(got - float(npz["sigma"])) <= 1e-10 * ref          # the executed reference's value
+    eng.close()
+
+
+def test_ruiz_matches_reference_pins(cfg1):
+    npz = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_functions.npz"))
+    eng = make_engine(cfg1)
+    rounds = eng.ruiz(20, 1e-6)
+    D_row, D_col = (t.cpu().numpy() for t in eng.scaling())
+    c_s, q_s, l_s, u_s = (t.cpu().numpy() for t in eng.problem())
+    assert rounds == 19
+    np.testing.assert_allclose(D_col, npz["ruiz_D_col"], rtol=1e-12)
+    np.testing.assert_allclose(D_row, npz["ruiz_D_row"], rtol=1e-12)
+    np.testing.assert_allclose(c_s, npz["ruiz_c"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(q_s, npz["ruiz_q"], rtol=1e-12, atol=1e-300)
+    Ks = eng.matrix().to_dense().cpu().numpy()
+    np.testing.assert_allclose(Ks.sum(axis=1), npz["ruiz_K_rowsum"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(Ks.sum(axis=0), npz["ruiz_K_colsum"], rtol=1e-10, atol=1e-12)
+    # the K^T copy was scaled identically: K^T w through the engine equals K_s^T w
+    w = np.random.default_rng(0).normal(size=cfg1.m)
+    np.testing.assert_allclose(eng.spmv(w, transpose=True).cpu().numpy(), Ks.T @ w, rtol=1e-10, atol=1e-11)
+    eng.close()
+
+
+def test_step_functions_reference_pins(cfg1, fp64_default):
+    """The drop-in step functions against outputs of the EXECUTED reference."""
+    from torchpdlp_b200 import primal_dual_hybrid_gradient_step as step
+    npz = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_functions.npz"))
+    c, K, q, m_ineq, l, u = cfg1.torch_tensors(layout="csr", device="cuda")
+    x = torch.from_numpy(npz["x"]).reshape(-1, 1).cuda()
+    y = torch.from_numpy(npz["y"]).reshape(-1, 1).cuda()
+    eta, omega = float(npz["eta"]), float(npz["omega"])
+    fx, fy, e1, e2 = step.fixed_one_step_pdhg(x.clone(), y.clone(), c, q, K, l, u, m_ineq, eta, omega, 1.0)
+    np.testing.assert_allclose(fx.cpu().numpy().ravel(), npz["fixed_x"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(fy.cpu().numpy().ravel(), npz["fixed_y"], rtol=0, atol=1e-11)
+    ax, ay, aw, an, j = step.adaptive_one_step_pdhg(x.clone(), y.clone(), c, q, K, l, u, m_ineq, eta, omega, 1.0,
+                                                    int(npz["adaptive_k"]), 0)
+    np.testing.assert_allclose(ax.cpu().numpy().ravel(), npz["adaptive_x"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ay.cpu().numpy().ravel(), npz["adaptive_y"], rtol=0, atol=1e-11)
+    assert abs(float(aw) - float(npz["adaptive_w"])) <= 1e-9 * float(npz["adaptive_w"])
+    assert abs(float(an) - float(npz["adaptive_next"])) <= 1e-9 * float(npz["adaptive_next"])
+    assert j == 1
+
+
+def test_bitwise_reproducible(cfg1):
+    """No atomics on data: two runs of 80 iterations give bit-identical iterates."""
+    outs = []
+    for _ in range(2):
+        eng = make_engine(cfg1)
+        eng.set_iterate(None, None)
+        eng.set_step(0.1, 0.5, 1.0, adaptive=True)
+        eng.iterate(40, save_previous=True, use_graph=True)
+        eng.iterate(40, save_previous=True, use_graph=False)
+        x, y = eng.get_iterate()
+        outs.append((x.cpu(), y.cpu(), eng.state().eta))
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]

@@ -1,0 +1,986 @@
+// pdlp_b200.cu -- engine, plan builder and C ABI (include/pdlp_b200.h).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/pdlp_b200.h"
+#include "pdlp_ops.cuh"
+
+using namespace pdlp;
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(PDLP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                     std::to_string(__LINE__) + ")");                              \
+  } while (0)
+
+extern "C" const char* pdlp_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------
+// plan: chunks + CTA ranges
+// ---------------------------------------------------------------------------
+struct HostPlan {
+  std::vector<Chunk> chunks;
+  std::vector<int> cta_begin;
+  int grid = 0;
+};
+
+static int floor_pow2(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// Greedy row packing: a chunk takes rows while nonzeros <= max_nnz and rows <= max_rows; a row longer than
+// max_nnz becomes a "long" chunk streamed from global memory by the whole CTA.  threads-per-row (power of two)
+// is chosen so that one pass of the CTA's NCONS lanes covers the chunk; when doubling it only costs a modest
+// truncation of the chunk, rows are dropped to make every lane busy.
+static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz, int max_rows, int ncons,
+                           int nwarps, int max_grid, double row_cost_nnz) {
+  HostPlan P;
+  int r = 0;
+  while (r < rows) {
+    const int len0 = rowptr[r + 1] - rowptr[r];
+    if (len0 > max_nnz) {
+      Chunk c{r, rowptr[r], rowptr[r + 1], CHUNK_LONG | 1u};
+      P.chunks.push_back(c);
+      ++r;
+      continue;
+    }
+    int e = r, nnz = 0;
+    while (e < rows && (e - r) < max_rows) {
+      const int len = rowptr[e + 1] - rowptr[e];
+      if (len > max_nnz || nnz + len > max_nnz) break;
+      nnz += len;
+      ++e;
+    }
+    int nr = e - r;
+    int tpr;
+    if (nr >= ncons) {
+      tpr = 1;
+      nr = (nr / ncons) * ncons;
+    } else {
+      tpr = std::min(32, floor_pow2(ncons / nr));
+      if (tpr < 32) {
+        const int nr_b = ncons / (2 * tpr);
+        if (nr_b * 3 >= nr * 2) {   // keep >= 2/3 of the rows and fill every lane
+          tpr *= 2;
+          nr = nr_b;
+        }
+      }
+      // rows are dealt to warps in equal slices; keep the slice a multiple of the groups per warp
+      (void)nwarps;
+    }
+    e = r + nr;
+    int tl = 0;
+    while ((1 << tl) < tpr) ++tl;
+    Chunk c{r, rowptr[r], rowptr[e], (uint32_t)nr | ((uint32_t)tl << 16)};
+    P.chunks.push_back(c);
+    r = e;
+  }
+  // contiguous ranges balanced by weight = nnz + row_cost_nnz * rows + fixed per-chunk cost
+  const int nc = (int)P.chunks.size();
+  std::vector<double> pre(nc + 1, 0.0);
+  for (int i = 0; i < nc; ++i) {
+    const Chunk& c = P.chunks[i];
+    const int nr = (c.meta & CHUNK_LONG) ? 1 : (int)(c.meta & 0xffff);
+    pre[i + 1] = pre[i] + (double)(c.nnz_end - c.nnz_begin) + row_cost_nnz * nr + 64.0;
+  }
+  P.grid = std::max(1, std::min(max_grid, nc));
+  P.cta_begin.resize(P.grid + 1);
+  P.cta_begin[0] = 0;
+  for (int p = 1; p < P.grid; ++p) {
+    const double target = pre[nc] * p / P.grid;
+    int lo = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+    lo = std::max(lo, P.cta_begin[p - 1]);
+    lo = std::min(lo, nc);
+    P.cta_begin[p] = lo;
+  }
+  P.cta_begin[P.grid] = nc;
+  return P;
+}
+
+// ---------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DeviceCsr {
+  int* rowptr = nullptr;
+  int* colidx = nullptr;
+  T* vals = nullptr;
+  Chunk* chunks = nullptr;
+  int* cta_begin = nullptr;
+  double* partials = nullptr;
+  unsigned int* ticket = nullptr;
+  int rows = 0, cols = 0, nnz = 0, grid = 0, nchunks = 0, nlong = 0;
+  CsrView<T> view() const {
+    return CsrView<T>{rowptr, colidx, vals, chunks, cta_begin, partials, ticket, rows};
+  }
+};
+
+struct pdlp_engine {
+  int dtype = PDLP_F64;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t m = 0, n = 0, m_ineq = 0, nnz = 0;
+  int sms = 0, ctas_per_sm = 2;
+  bool scaled = false;
+  bool have_prev = false;
+  bool infeas = false;    // host mirror of Scalars::infeas_detect
+  void* impl = nullptr;   // EngineT<T>*
+};
+
+template <typename T>
+struct EngineT {
+  pdlp_engine* base;
+  DeviceCsr<T> K, Kt;
+  T *c = nullptr, *q = nullptr, *l = nullptr, *u = nullptr;
+  Pair<T>* xp = nullptr;
+  T *y = nullptr, *xsum = nullptr, *ysum = nullptr, *xlast = nullptr, *ylast = nullptr;
+  Quad<T>*X4 = nullptr, *Y4 = nullptr;
+  T *drow = nullptr, *dcol = nullptr;     // accumulated scalings (ones until pdlp_ruiz)
+  T *tmp_n = nullptr, *tmp_m = nullptr, *tmp_n2 = nullptr;
+  T *kty_old = nullptr, *lam_prev = nullptr;   // infeasibility detection state
+  Scalars* S = nullptr;
+  double* ew_partials = nullptr;
+  unsigned int* ew_ticket = nullptr;
+  int ew_grid = 0;
+  // cached graphs for pdlp_iterate
+  struct GraphEntry { int n_iters; int save_prev; int infeas; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs;
+  std::vector<void*> allocs;
+};
+
+template <typename T>
+static int dev_alloc(EngineT<T>* E, void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes ? bytes : 16));
+  E->allocs.push_back(*p);
+  return 0;
+}
+#define ALLOC(ptr, count)                                                                  \
+  do {                                                                                     \
+    int rc_ = dev_alloc(E, (void**)&(ptr), sizeof(*(ptr)) * (size_t)(count));              \
+    if (rc_) return rc_;                                                                   \
+  } while (0)
+
+template <class Op>
+static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st) {
+  using T = typename Op::value_type;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         StreamCfg<T>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  stream_kernel<Op><<<A.grid, StreamCfg<T>::NT, StreamCfg<T>::SMEM_BYTES, st>>>(A.view(), op);
+  return cudaGetLastError();
+}
+
+template <typename T>
+static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nnz, const int32_t* rowptr,
+                      const int32_t* colidx, const void* vals, double row_cost_nnz) {
+  cudaStream_t st = E->base->stream;
+  A.rows = rows;
+  A.cols = cols;
+  A.nnz = nnz;
+  const size_t pad = 16;
+  ALLOC(A.rowptr, rows + 1 + pad);
+  ALLOC(A.colidx, nnz + pad);
+  ALLOC(A.vals, nnz + pad);
+  CU(cudaMemsetAsync(A.rowptr, 0, sizeof(int) * (rows + 1 + pad), st));
+  CU(cudaMemsetAsync(A.colidx, 0, sizeof(int) * (nnz + pad), st));
+  CU(cudaMemsetAsync(A.vals, 0, sizeof(T) * (nnz + pad), st));
+  CU(cudaMemcpyAsync(A.rowptr, rowptr, sizeof(int) * (rows + 1), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(A.colidx, colidx, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(A.vals, vals, sizeof(T) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
+  std::vector<int> h_rowptr(rows + 1);
+  CU(cudaMemcpyAsync(h_rowptr.data(), A.rowptr, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (h_rowptr[0] != 0 || h_rowptr[rows] != nnz) return fail(PDLP_ERR_INVALID, "rowptr does not span [0, nnz]");
+  for (int r = 0; r < rows; ++r)
+    if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
+  using Cfg = StreamCfg<T>;
+  HostPlan P = build_plan(h_rowptr, rows, Cfg::MAX_CHUNK_NNZ, Cfg::MAX_CHUNK_ROWS, Cfg::NCONS, Cfg::NWARPS,
+                          E->base->sms * E->base->ctas_per_sm, row_cost_nnz);
+  A.grid = P.grid;
+  A.nchunks = (int)P.chunks.size();
+  A.nlong = 0;
+  for (const Chunk& c : P.chunks) A.nlong += (c.meta & CHUNK_LONG) ? 1 : 0;
+  ALLOC(A.chunks, P.chunks.size() + 1);
+  ALLOC(A.cta_begin, P.cta_begin.size());
+  ALLOC(A.partials, (size_t)P.grid * MAX_RED);
+  ALLOC(A.ticket, 1);
+  CU(cudaMemcpyAsync(A.chunks, P.chunks.data(), sizeof(Chunk) * P.chunks.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.cta_begin, P.cta_begin.data(), sizeof(int) * P.cta_begin.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(A.ticket, 0, sizeof(unsigned int), st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static inline int ew_blocks(int64_t len, int sms) {
+  int64_t b = (len + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sms * 8));
+}
+
+template <typename T>
+static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
+                         const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
+                         const void* q, const void* l, const void* u) {
+  EngineT<T>* E = new EngineT<T>();
+  E->base = B;
+  B->impl = E;
+  const int m = (int)B->m, n = (int)B->n, nnz = (int)B->nnz;
+  cudaStream_t st = B->stream;
+  // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
+  const double per_nnz = sizeof(T) + 4.0;
+  int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals, 5.0 * sizeof(T) / per_nnz);
+  if (rc) return rc;
+  rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals, 8.0 * sizeof(T) / per_nnz);
+  if (rc) return rc;
+  ALLOC(E->c, n); ALLOC(E->l, n); ALLOC(E->u, n); ALLOC(E->q, m);
+  ALLOC(E->xp, n); ALLOC(E->xsum, n); ALLOC(E->xlast, n); ALLOC(E->X4, n);
+  ALLOC(E->y, m); ALLOC(E->ysum, m); ALLOC(E->ylast, m); ALLOC(E->Y4, m);
+  ALLOC(E->drow, m); ALLOC(E->dcol, n);
+  ALLOC(E->tmp_n, n); ALLOC(E->tmp_n2, n); ALLOC(E->tmp_m, m);
+  ALLOC(E->kty_old, n); ALLOC(E->lam_prev, n);
+  CU(cudaMemsetAsync(E->kty_old, 0, sizeof(T) * n, st));
+  CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
+  ALLOC(E->S, 1);
+  E->ew_grid = B->sms * 4;
+  ALLOC(E->ew_partials, 2 * E->ew_grid);
+  ALLOC(E->ew_ticket, 1);
+  CU(cudaMemsetAsync(E->ew_ticket, 0, sizeof(unsigned int), st));
+  CU(cudaMemcpyAsync(E->c, c, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(E->l, l, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(E->u, u, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(E->q, q, sizeof(T) * m, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemsetAsync(E->X4, 0, sizeof(Quad<T>) * n, st));
+  CU(cudaMemsetAsync(E->Y4, 0, sizeof(Quad<T>) * m, st));
+  fill_kernel<T><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->drow, T(1), m);
+  fill_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->dcol, T(1), n);
+  set_iterate_kernel<T><<<ew_blocks(std::max(m, n), B->sms), 256, 0, st>>>(nullptr, nullptr, E->xp, E->y, E->xsum,
+                                                                          E->ysum, E->xlast, E->ylast, n, m);
+  CU(cudaGetLastError());
+  Scalars h;
+  memset(&h, 0, sizeof(h));
+  h.eta = 1.0; h.omega = 1.0; h.theta = 1.0; h.tol = 1e-4; h.infeas_tol = 1e-4;
+  h.m_ineq = (int)B->m_ineq;
+  CU(cudaMemcpyAsync(E->S, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template <typename T>
+static void engine_destroy(pdlp_engine* B) {
+  EngineT<T>* E = (EngineT<T>*)B->impl;
+  if (!E) return;
+  for (auto& g : E->graphs) cudaGraphExecDestroy(g.exec);
+  for (void* p : E->allocs) cudaFree(p);
+  delete E;
+  B->impl = nullptr;
+}
+
+// ||q||, ||c|| of the CURRENT (possibly scaled) problem -> Scalars (primal_dual_hybrid_gradient.py:19-20)
+template <typename T>
+static int refresh_norms(EngineT<T>* E) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  sumsq_kernel<T><<<1, 1024, 0, st>>>(E->q, (int)B->m, E->S, 0);
+  sumsq_kernel<T><<<1, 1024, 0, st>>>(E->c, (int)B->n, E->S, 1);
+  CU(cudaGetLastError());
+  double sc[2];
+  CU(cudaMemcpyAsync(sc, (char*)E->S + offsetof(Scalars, scratch), sizeof(sc), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  double nrm[2] = {sqrt(sc[0]), sqrt(sc[1])};
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, q_norm), &nrm[0], sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, c_norm), &nrm[1], sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// hot loop
+// ---------------------------------------------------------------------------
+template <typename T, bool SP, bool INF>
+static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
+  PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
+  cudaError_t e = launch_stream(E->Kt, p, st);
+  if (e != cudaSuccess) return e;
+  DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+  e = launch_stream(E->K, d, st);
+  if (e != cudaSuccess) return e;
+  if (INF) {
+    InfeasColsOp<T> f{E->y, E->c, E->l, E->u, E->kty_old, E->lam_prev, E->S};
+    e = launch_stream(E->Kt, f, st);
+  }
+  return e;
+}
+
+template <typename T>
+static cudaError_t enqueue_iterations(EngineT<T>* E, int n_iters, int save_prev, cudaStream_t st) {
+  const bool inf = E->base->infeas;
+  for (int i = 0; i < n_iters; ++i) {
+    const bool sp = save_prev && (i == n_iters - 1);
+    cudaError_t e;
+    if (inf) e = sp ? enqueue_one<T, true, true>(E, st) : enqueue_one<T, false, true>(E, st);
+    else e = sp ? enqueue_one<T, true, false>(E, st) : enqueue_one<T, false, false>(E, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <class Op>
+static cudaError_t prep_kernel() {
+  return cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              StreamCfg<typename Op::value_type>::SMEM_BYTES);
+}
+
+template <typename T>
+static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_graph) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  if (n_iters <= 0) return 0;
+  if (save_prev) B->have_prev = true;
+  if (!use_graph || n_iters < 2) {
+    CU(enqueue_iterations<T>(E, n_iters, save_prev, st));
+    return 0;
+  }
+  const int inf = B->infeas ? 1 : 0;
+  for (auto& g : E->graphs)
+    if (g.n_iters == n_iters && g.save_prev == (save_prev ? 1 : 0) && g.infeas == inf) {
+      CU(cudaGraphLaunch(g.exec, st));
+      return 0;
+    }
+  // first use: set the kernels' attributes outside capture, then capture the whole block
+  cudaStream_t cap;
+  CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  CU((prep_kernel<PrimalOp<T, true, false>>()));
+  CU((prep_kernel<PrimalOp<T, false, false>>()));
+  CU((prep_kernel<PrimalOp<T, true, true>>()));
+  CU((prep_kernel<PrimalOp<T, false, true>>()));
+  CU((prep_kernel<DualOp<T, true, false>>()));
+  CU((prep_kernel<DualOp<T, false, false>>()));
+  CU((prep_kernel<DualOp<T, true, true>>()));
+  CU((prep_kernel<DualOp<T, false, true>>()));
+  CU((prep_kernel<InfeasColsOp<T>>()));
+  CU(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = enqueue_iterations<T>(E, n_iters, save_prev, cap);
+  cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    return fail(PDLP_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+  }
+  cudaGraphExec_t exec = nullptr;
+  CU(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  cudaStreamDestroy(cap);
+  E->graphs.push_back({n_iters, save_prev ? 1 : 0, inf, exec});
+  CU(cudaGraphLaunch(exec, st));
+  return 0;
+}
+
+template <typename T>
+static int enqueue_kkt(EngineT<T>* E, cudaStream_t st) {
+  pdlp_engine* B = E->base;
+  KktColsOp<T> a{E->Y4, E->X4, E->c, E->l, E->u, B->scaled ? E->dcol : nullptr, E->S};
+  CU(launch_stream(E->Kt, a, st));
+  KktRowsOp<T> b{E->X4, E->Y4, E->q, B->scaled ? E->drow : nullptr, E->S, 0};
+  CU(launch_stream(E->K, b, st));
+  return 0;
+}
+
+static void fill_residuals(pdlp_residuals* o, const Resid& r) {
+  o->pr = r.pr; o->dr = r.dr; o->gap = r.gap; o->prim_obj = r.prim_obj; o->adj_dual = r.adj_dual; o->kkt = r.kkt;
+  o->pr_unscaled = r.pr_u; o->dr_unscaled = r.dr_u;
+}
+
+template <typename T>
+static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m;
+  const int have_prev = (B->have_prev && !force) ? 1 : 0;
+  flush_kernel<T><<<ew_blocks(std::max(n, m), B->sms), 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, n, m,
+                                                                     E->S, have_prev);
+  CU(cudaGetLastError());
+  int rc = enqueue_kkt<T>(E, st);
+  if (rc) return rc;
+  decide_kernel<<<1, 1, 0, st>>>(E->S, force);
+  apply_restart_kernel<T><<<E->ew_grid, 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, E->xlast, E->ylast,
+                                                      n, m, E->S, E->ew_partials, E->ew_ticket);
+  post_restart_kernel<<<1, 1, 0, st>>>(E->S, B->scaled ? 1 : 0);
+  CU(cudaGetLastError());
+  B->have_prev = false;
+  Scalars h;
+  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out) {
+    out->kind = h.chk_kind;
+    out->use_average = h.chk_use_avg;
+    out->t = h.chk_t;
+    out->solved = h.chk_solved;
+    out->k = h.chk_k;
+    out->omega = h.omega;
+    out->kkt_current = h.kkt_cur;
+    out->kkt_average = h.kkt_avg;
+    out->kkt_previous = h.kkt_prev;
+    out->kkt_first_new = h.kkt_first;
+    fill_residuals(&out->point, h.point);
+  }
+  return 0;
+}
+
+template <typename T>
+static int engine_kkt(EngineT<T>* E, const void* x, const void* y, double omega, pdlp_residuals* out) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m;
+  pack3_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>((const T*)x, E->X4, n);
+  pack3_kernel<T><<<ew_blocks(m, B->sms), 256, 0, st>>>((const T*)y, E->Y4, m);
+  CU(cudaGetLastError());
+  // the column-side finalize zeroes w_pending (it normally follows a flush): preserve it
+  double wp;
+  CU(cudaMemcpyAsync(&wp, (char*)E->S + offsetof(Scalars, w_pending), sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int rc = enqueue_kkt<T>(E, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, w_pending), &wp, sizeof(double), cudaMemcpyHostToDevice, st));
+  Scalars h;
+  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  B->have_prev = false;
+  const Resid r = make_resid(h.sums[IT_CUR], omega);
+  fill_residuals(out, r);
+  return 0;
+}
+
+template <typename T>
+static int engine_power_iteration(EngineT<T>* E, const void* b0, int iters, double* sigma) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n;
+  T* b = E->tmp_n;
+  T* v = E->tmp_n2;
+  T* w = E->tmp_m;
+  CU(cudaMemcpyAsync(b, b0, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < iters; ++i) {
+    SpmvOp<T, false> f{b, w, E->S, 2};
+    CU(launch_stream(E->K, f, st));
+    SpmvOp<T, true> g{w, v, E->S, 2};
+    CU(launch_stream(E->Kt, g, st));
+    normalize_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(v, b, n, E->S, 2);
+    CU(cudaGetLastError());
+  }
+  SpmvOp<T, true> f{b, w, E->S, 3};
+  CU(launch_stream(E->K, f, st));
+  double ss;
+  CU(cudaMemcpyAsync(&ss, (char*)E->S + offsetof(Scalars, scratch) + 3 * sizeof(double), sizeof(double),
+                     cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *sigma = sqrt(ss);
+  return 0;
+}
+
+template <typename T>
+static int read_scratch(EngineT<T>* E, int slot, double* out) {
+  cudaStream_t st = E->base->stream;
+  CU(cudaMemcpyAsync(out, (char*)E->S + offsetof(Scalars, scratch) + slot * sizeof(double), sizeof(double),
+                     cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template <typename T>
+static int apply_vector_scaling(EngineT<T>* E, const T* drow_step, const T* dcol_step) {
+  // c *= D, q *= D, l /= D, u /= D for the scaling accumulated in THIS call (enhancements.py:64-67)
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m;
+  vec_scale_kernel<T, 0><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->c, dcol_step, n);
+  vec_scale_kernel<T, 0><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->q, drow_step, m);
+  vec_scale_kernel<T, 1><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->l, dcol_step, n);
+  vec_scale_kernel<T, 1><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->u, dcol_step, n);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int engine_ruiz(EngineT<T>* E, int max_iter, double eps, int* rounds_out) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m, nnz = (int)B->nnz;
+  const int wb_m = ew_blocks((int64_t)m * 32, B->sms), wb_n = ew_blocks((int64_t)n * 32, B->sms);
+  const int eb = ew_blocks(nnz, B->sms);
+  // this call's own accumulators (the reference starts from ones, :46-47)
+  T* drs = nullptr; T* dcs = nullptr;
+  CU(cudaMalloc(&drs, sizeof(T) * std::max(m, 1)));
+  CU(cudaMalloc(&dcs, sizeof(T) * std::max(n, 1)));
+  fill_kernel<T><<<ew_blocks(m, B->sms), 256, 0, st>>>(drs, T(1), m);
+  fill_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(dcs, T(1), n);
+  int rounds = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    ++rounds;
+    row_absreduce_kernel<T, 0><<<wb_m, 256, 0, st>>>(E->K.rowptr, E->K.vals, m, E->tmp_m);
+    ruiz_fix_kernel<T><<<1, 1024, 0, st>>>(E->tmp_m, drs, m, (T)eps, E->S, 4);
+    scale_rows_kernel<T><<<wb_m, 256, 0, st>>>(E->K.rowptr, E->K.vals, m, E->tmp_m);
+    scale_cols_kernel<T><<<eb, 256, 0, st>>>(E->Kt.colidx, E->Kt.vals, nnz, E->tmp_m);
+    row_absreduce_kernel<T, 0><<<wb_n, 256, 0, st>>>(E->Kt.rowptr, E->Kt.vals, n, E->tmp_n);
+    ruiz_fix_kernel<T><<<1, 1024, 0, st>>>(E->tmp_n, dcs, n, (T)eps, E->S, 5);
+    scale_rows_kernel<T><<<wb_n, 256, 0, st>>>(E->Kt.rowptr, E->Kt.vals, n, E->tmp_n);
+    scale_cols_kernel<T><<<eb, 256, 0, st>>>(E->K.colidx, E->K.vals, nnz, E->tmp_n);
+    CU(cudaGetLastError());
+    double dev;
+    int rc = read_scratch<T>(E, 4, &dev);   // max |1 - row_norms| (:60-61 tests the row norms twice)
+    if (rc) return rc;
+    if (dev < eps) break;
+  }
+  int rc = apply_vector_scaling<T>(E, drs, dcs);
+  if (rc) return rc;
+  vec_scale_kernel<T, 0><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->drow, drs, m);
+  vec_scale_kernel<T, 0><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->dcol, dcs, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  cudaFree(drs);
+  cudaFree(dcs);
+  B->scaled = true;
+  if (rounds_out) *rounds_out = rounds;
+  return refresh_norms<T>(E);
+}
+
+template <typename T>
+static int engine_pock_chambolle(EngineT<T>* E) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m, nnz = (int)B->nnz;
+  const int wb_m = ew_blocks((int64_t)m * 32, B->sms), wb_n = ew_blocks((int64_t)n * 32, B->sms);
+  const int eb = ew_blocks(nnz, B->sms);
+  T* drs = nullptr; T* dcs = nullptr;
+  CU(cudaMalloc(&drs, sizeof(T) * std::max(m, 1)));
+  CU(cudaMalloc(&dcs, sizeof(T) * std::max(n, 1)));
+  fill_kernel<T><<<ew_blocks(m, B->sms), 256, 0, st>>>(drs, T(1), m);
+  fill_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(dcs, T(1), n);
+  // both L1 norms are taken on the input matrix, then applied
+  row_absreduce_kernel<T, 1><<<wb_m, 256, 0, st>>>(E->K.rowptr, E->K.vals, m, E->tmp_m);
+  row_absreduce_kernel<T, 1><<<wb_n, 256, 0, st>>>(E->Kt.rowptr, E->Kt.vals, n, E->tmp_n);
+  ruiz_fix_kernel<T><<<1, 1024, 0, st>>>(E->tmp_m, drs, m, (T)1e-6, E->S, 4);
+  ruiz_fix_kernel<T><<<1, 1024, 0, st>>>(E->tmp_n, dcs, n, (T)1e-6, E->S, 5);
+  scale_rows_kernel<T><<<wb_m, 256, 0, st>>>(E->K.rowptr, E->K.vals, m, E->tmp_m);
+  scale_cols_kernel<T><<<eb, 256, 0, st>>>(E->Kt.colidx, E->Kt.vals, nnz, E->tmp_m);
+  scale_rows_kernel<T><<<wb_n, 256, 0, st>>>(E->Kt.rowptr, E->Kt.vals, n, E->tmp_n);
+  scale_cols_kernel<T><<<eb, 256, 0, st>>>(E->K.colidx, E->K.vals, nnz, E->tmp_n);
+  CU(cudaGetLastError());
+  int rc = apply_vector_scaling<T>(E, drs, dcs);
+  if (rc) return rc;
+  vec_scale_kernel<T, 0><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->drow, drs, m);
+  vec_scale_kernel<T, 0><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->dcol, dcs, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  cudaFree(drs);
+  cudaFree(dcs);
+  B->scaled = true;
+  return refresh_norms<T>(E);
+}
+
+template <typename T>
+static int engine_objective(EngineT<T>* E, double* out) {
+  pdlp_engine* B = E->base;
+  objective_kernel<T><<<1, 1024, 0, B->stream>>>(E->c, E->xp, (int)B->n, E->S, 7);
+  CU(cudaGetLastError());
+  return read_scratch<T>(E, 7, out);
+}
+
+// ---------------------------------------------------------------------------
+// whole solve: primal_dual_hybrid_gradient.py:54-181 with the reference's k / n / j accounting
+// ---------------------------------------------------------------------------
+template <typename T>
+static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_result* res, pdlp_check* trace) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto elapsed = [&]() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() + o->time_used;
+  };
+  cudaEvent_t ev0, ev1;
+  CU(cudaEventCreate(&ev0));
+  CU(cudaEventCreate(&ev1));
+  CU(cudaEventRecord(ev0, st));
+  const int period = o->restart_period > 0 ? o->restart_period : 40;
+  Scalars h;
+  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int64_t k = h.k, j = 0;
+  int n_restart = 0, status = 1, n_trace = 0;
+  const bool infeas = h.infeas_detect != 0;
+  double prim_obj = NAN;
+  bool timed_out = false, detected = false;
+  while (j < o->max_kkt && status == 1) {
+    int t = 0;
+    bool restarted = false;
+    while (j < o->max_kkt) {
+      if (elapsed() >= o->time_limit) { timed_out = true; break; }
+      // iterations until the next restart test, limited by the KKT-pass budget (:67: guard before every iteration)
+      int want = period - (t % period);
+      int iters = 0;
+      int64_t jj = j, kk = k;
+      while (iters < want && jj < o->max_kkt) {
+        ++kk;
+        jj += 1 + ((infeas && kk > 1) ? 1 : 0);
+        ++iters;
+      }
+      const int at_check = ((t + iters) % period == 0) ? 1 : 0;
+      int rc = engine_iterate<T>(E, iters, at_check, o->use_graph);
+      if (rc) return rc;
+      if (infeas) {
+        // :89-101: the device raised `stop` at the iteration where a certificate test passed
+        Scalars hs;
+        CU(cudaMemcpyAsync(&hs, E->S, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (hs.infeas) {
+          while (k < hs.infeas_k) { ++k; j += 1 + (k > 1 ? 1 : 0); }
+          status = hs.infeas == 2 ? 3 : 4;
+          rc = engine_objective<T>(E, &prim_obj);
+          if (rc) return rc;
+          detected = true;
+          break;
+        }
+      }
+      j = jj; k = kk; t += iters;
+      if (at_check) {
+        pdlp_check chk;
+        rc = engine_restart_check<T>(E, 0, &chk);
+        if (rc) return rc;
+        j += 3;                                    // :128
+        if (chk.kind != PDLP_RESTART_NONE) {
+          restarted = true;
+          ++n_restart;
+          j += 2;                                  // :154, :165
+          prim_obj = chk.point.prim_obj;
+          if (trace && n_trace < o->max_trace) trace[n_trace++] = chk;
+          if (chk.solved) status = 0;
+          break;
+        }
+      }
+    }
+    if (timed_out) { status = 2; break; }
+    if (detected) break;
+    if (!restarted) {
+      // loop left through the guard: the epilogue runs on the current iterate (:148-177)
+      pdlp_check chk;
+      int rc = engine_restart_check<T>(E, 1, &chk);
+      if (rc) return rc;
+      ++n_restart;
+      j += 2;
+      prim_obj = chk.point.prim_obj;
+      if (trace && n_trace < o->max_trace) trace[n_trace++] = chk;
+      if (chk.solved) status = 0;
+    }
+  }
+  CU(cudaEventRecord(ev1, st));
+  CU(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  res->k = k; res->j = j; res->n = n_restart; res->status = status; res->prim_obj = prim_obj;
+  res->seconds = elapsed(); res->device_ms = ms; res->n_trace = n_trace; res->reserved = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+#define DISPATCH(h, fn, ...)                                                         \
+  ((h)->dtype == PDLP_F64 ? fn<double>((EngineT<double>*)(h)->impl, ##__VA_ARGS__)   \
+                          : fn<float>((EngineT<float>*)(h)->impl, ##__VA_ARGS__))
+
+#define CHECK_HANDLE(h)                                              \
+  do {                                                               \
+    if (!(h) || !(h)->impl) return fail(PDLP_ERR_INVALID, "null handle"); \
+    cudaError_t e_ = cudaSetDevice((h)->device);                     \
+    if (e_ != cudaSuccess) return fail(PDLP_ERR_CUDA, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                           const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
+                           const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
+                           const void* q, const void* l, const void* u, void* stream) {
+  if (!out) return fail(PDLP_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (dtype != PDLP_F64 && dtype != PDLP_F32) return fail(PDLP_ERR_INVALID, "dtype must be PDLP_F64 or PDLP_F32");
+  if (m <= 0 || n <= 0 || m_ineq < 0 || m_ineq > m || nnz < 0) return fail(PDLP_ERR_INVALID, "bad dimensions");
+  if (m >= INT32_MAX - 64 || n >= INT32_MAX - 64 || nnz >= INT32_MAX - 64)
+    return fail(PDLP_ERR_INVALID, "dimensions exceed int32 indexing");
+  if (!K_rowptr || !Kt_rowptr || !c || !q || !l || !u || (nnz > 0 && (!K_colidx || !K_vals || !Kt_colidx || !Kt_vals)))
+    return fail(PDLP_ERR_INVALID, "null problem pointer");
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 9) return fail(PDLP_ERR_CUDA, "pdlp_b200 needs TMA bulk copies (built for sm_100a)");
+  pdlp_engine* B = new pdlp_engine();
+  B->dtype = dtype; B->device = dev; B->stream = (cudaStream_t)stream;
+  B->m = m; B->n = n; B->m_ineq = m_ineq; B->nnz = nnz;
+  B->sms = prop.multiProcessorCount;
+  int rc = dtype == PDLP_F64
+               ? engine_create<double>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u)
+               : engine_create<float>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u);
+  if (!rc) rc = dtype == PDLP_F64 ? refresh_norms<double>((EngineT<double>*)B->impl)
+                                  : refresh_norms<float>((EngineT<float>*)B->impl);
+  if (rc) {
+    if (dtype == PDLP_F64) engine_destroy<double>(B); else engine_destroy<float>(B);
+    delete B;
+    return rc;
+  }
+  *out = B;
+  return 0;
+}
+
+extern "C" int pdlp_destroy(pdlp_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->dtype == PDLP_F64) engine_destroy<double>(h); else engine_destroy<float>(h);
+  delete h;
+  return 0;
+}
+
+extern "C" int64_t pdlp_bytes_per_iteration(pdlp_handle h) {
+  if (!h) return 0;
+  const int64_t vb = h->dtype == PDLP_F64 ? 8 : 4;
+  return 2 * (vb + 4) * h->nnz + 4 * (h->m + h->n + 2) + 9 * vb * h->n + 6 * vb * h->m;
+}
+
+template <typename T>
+static int t_set_iterate(EngineT<T>* E, const void* x, const void* y) {
+  pdlp_engine* B = E->base;
+  const int n = (int)B->n, m = (int)B->m;
+  set_iterate_kernel<T><<<ew_blocks(std::max(m, n), B->sms), 256, 0, B->stream>>>(
+      (const T*)x, (const T*)y, E->xp, E->y, E->xsum, E->ysum, E->xlast, E->ylast, n, m);
+  CU(cudaGetLastError());
+  // :58-64 / :104-112: fresh epoch
+  const double z[2] = {0.0, 0.0};
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, w_pending), z, 2 * sizeof(double), cudaMemcpyHostToDevice, B->stream));
+  const int zi = 0;
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, t), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, infeas), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, infeas_k), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * (size_t)n, B->stream));   // pdlp :39-40
+  CU(cudaStreamSynchronize(B->stream));
+  B->have_prev = false;
+  return 0;
+}
+extern "C" int pdlp_set_iterate(pdlp_handle h, const void* x, const void* y) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, t_set_iterate, x, y);
+}
+
+template <typename T>
+static int t_get_iterate(EngineT<T>* E, void* x, void* y) {
+  pdlp_engine* B = E->base;
+  get_iterate_kernel<T><<<ew_blocks(std::max(B->m, B->n), B->sms), 256, 0, B->stream>>>(E->xp, E->y, (T*)x, (T*)y,
+                                                                                        (int)B->n, (int)B->m);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int pdlp_get_iterate(pdlp_handle h, void* x, void* y) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, t_get_iterate, x, y);
+}
+
+template <typename T>
+static int t_get_average(EngineT<T>* E, void* x, void* y) {
+  pdlp_engine* B = E->base;
+  get_average_kernel<T><<<ew_blocks(std::max(B->m, B->n), B->sms), 256, 0, B->stream>>>(
+      E->xp, E->y, E->xsum, E->ysum, (T*)x, (T*)y, (int)B->n, (int)B->m, E->S);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int pdlp_get_average(pdlp_handle h, void* x, void* y) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, t_get_average, x, y);
+}
+
+template <typename T>
+static int t_get_scalars(EngineT<T>* E, Scalars* hs) {
+  CU(cudaMemcpyAsync(hs, E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, E->base->stream));
+  CU(cudaStreamSynchronize(E->base->stream));
+  return 0;
+}
+template <typename T>
+static int t_put_scalars(EngineT<T>* E, const Scalars* hs) {
+  CU(cudaMemcpyAsync(E->S, hs, sizeof(Scalars), cudaMemcpyHostToDevice, E->base->stream));
+  CU(cudaStreamSynchronize(E->base->stream));
+  return 0;
+}
+
+extern "C" int pdlp_set_step(pdlp_handle h, double eta, double omega, double theta, int adaptive) {
+  CHECK_HANDLE(h);
+  if (!(eta > 0.0) || !(omega > 0.0)) return fail(PDLP_ERR_INVALID, "eta and omega must be positive");
+  Scalars s;
+  int rc = DISPATCH(h, t_get_scalars, &s);
+  if (rc) return rc;
+  s.eta = eta; s.omega = omega; s.theta = theta; s.adaptive = adaptive ? 1 : 0;
+  return DISPATCH(h, t_put_scalars, &s);
+}
+
+extern "C" int pdlp_set_options(pdlp_handle h, double tol, int primal_update, int infeasibility_detect,
+                                double infeas_tol) {
+  CHECK_HANDLE(h);
+  Scalars s;
+  int rc = DISPATCH(h, t_get_scalars, &s);
+  if (rc) return rc;
+  s.tol = tol; s.primal_update = primal_update ? 1 : 0; s.infeas_detect = infeasibility_detect ? 1 : 0;
+  s.infeas_tol = infeas_tol;
+  h->infeas = infeasibility_detect != 0;
+  return DISPATCH(h, t_put_scalars, &s);
+}
+
+extern "C" int pdlp_get_state(pdlp_handle h, pdlp_state* o) {
+  CHECK_HANDLE(h);
+  if (!o) return fail(PDLP_ERR_INVALID, "host_out is null");
+  Scalars s;
+  int rc = DISPATCH(h, t_get_scalars, &s);
+  if (rc) return rc;
+  o->eta = s.eta; o->omega = s.omega; o->theta = s.theta; o->eta_sum = s.eta_sum; o->last_weight = s.last_weight;
+  o->dx2 = s.dx2; o->dy2 = s.dy2; o->inter = s.inter; o->kkt_first = s.kkt_first; o->q_norm = s.q_norm;
+  o->c_norm = s.c_norm; o->k = s.k; o->t = s.t; o->n_restarts = s.n_restarts; o->infeas = s.infeas;
+  o->infeas_k = s.infeas_k; o->solved = s.solved; o->reserved = 0;
+  return 0;
+}
+
+extern "C" int pdlp_set_counters(pdlp_handle h, int64_t k, int32_t t) {
+  CHECK_HANDLE(h);
+  Scalars s;
+  int rc = DISPATCH(h, t_get_scalars, &s);
+  if (rc) return rc;
+  s.k = k; s.t = t;
+  return DISPATCH(h, t_put_scalars, &s);
+}
+
+extern "C" int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int use_graph) {
+  CHECK_HANDLE(h);
+  if (n_iters < 0) return fail(PDLP_ERR_INVALID, "n_iters < 0");
+  return DISPATCH(h, engine_iterate, n_iters, save_previous, use_graph);
+}
+
+extern "C" int pdlp_restart_check(pdlp_handle h, int force, pdlp_check* host_out) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, engine_restart_check, force, host_out);
+}
+
+extern "C" int pdlp_kkt(pdlp_handle h, const void* x, const void* y, double omega, pdlp_residuals* host_out) {
+  CHECK_HANDLE(h);
+  if (!x || !y || !host_out) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, engine_kkt, x, y, omega, host_out);
+}
+
+extern "C" int pdlp_power_iteration(pdlp_handle h, const void* b0, int iters, double* host_sigma) {
+  CHECK_HANDLE(h);
+  if (!b0 || !host_sigma || iters < 0) return fail(PDLP_ERR_INVALID, "bad argument");
+  return DISPATCH(h, engine_power_iteration, b0, iters, host_sigma);
+}
+
+template <typename T>
+static int t_spmv(EngineT<T>* E, int transpose, const void* in, void* out) {
+  SpmvOp<T, false> f{(const T*)in, (T*)out, E->S, 6};
+  CU(launch_stream(transpose ? E->Kt : E->K, f, E->base->stream));
+  return 0;
+}
+extern "C" int pdlp_spmv(pdlp_handle h, int transpose, const void* in, void* out) {
+  CHECK_HANDLE(h);
+  if (!in || !out) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, t_spmv, transpose, in, out);
+}
+
+extern "C" int pdlp_ruiz(pdlp_handle h, int max_iter, double eps, int* host_rounds) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, engine_ruiz, max_iter, eps, host_rounds);
+}
+extern "C" int pdlp_pock_chambolle(pdlp_handle h) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, engine_pock_chambolle);
+}
+
+template <typename T>
+static int t_copy_out(EngineT<T>* E, void* dst, const T* src, int64_t len) {
+  if (!dst) return 0;
+  CU(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)len, cudaMemcpyDeviceToDevice, E->base->stream));
+  return 0;
+}
+extern "C" int pdlp_get_scaling(pdlp_handle h, void* D_row, void* D_col) {
+  CHECK_HANDLE(h);
+  int rc = h->dtype == PDLP_F64 ? t_copy_out<double>((EngineT<double>*)h->impl, D_row, ((EngineT<double>*)h->impl)->drow, h->m)
+                                : t_copy_out<float>((EngineT<float>*)h->impl, D_row, ((EngineT<float>*)h->impl)->drow, h->m);
+  if (rc) return rc;
+  return h->dtype == PDLP_F64 ? t_copy_out<double>((EngineT<double>*)h->impl, D_col, ((EngineT<double>*)h->impl)->dcol, h->n)
+                              : t_copy_out<float>((EngineT<float>*)h->impl, D_col, ((EngineT<float>*)h->impl)->dcol, h->n);
+}
+
+template <typename T>
+static int t_set_scaling(EngineT<T>* E, const void* drow, const void* dcol) {
+  pdlp_engine* B = E->base;
+  CU(cudaMemcpyAsync(E->drow, drow, sizeof(T) * (size_t)B->m, cudaMemcpyDeviceToDevice, B->stream));
+  CU(cudaMemcpyAsync(E->dcol, dcol, sizeof(T) * (size_t)B->n, cudaMemcpyDeviceToDevice, B->stream));
+  B->scaled = true;
+  return 0;
+}
+extern "C" int pdlp_set_scaling(pdlp_handle h, const void* D_row, const void* D_col) {
+  CHECK_HANDLE(h);
+  if (!D_row || !D_col) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, t_set_scaling, D_row, D_col);
+}
+
+template <typename T>
+static int t_get_problem(EngineT<T>* E, void* c, void* q, void* l, void* u) {
+  int rc = t_copy_out<T>(E, c, E->c, E->base->n);
+  if (!rc) rc = t_copy_out<T>(E, q, E->q, E->base->m);
+  if (!rc) rc = t_copy_out<T>(E, l, E->l, E->base->n);
+  if (!rc) rc = t_copy_out<T>(E, u, E->u, E->base->n);
+  return rc;
+}
+extern "C" int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, t_get_problem, c, q, l, u);
+}
+
+template <typename T>
+static int t_get_matrix_values(EngineT<T>* E, void* vals) {
+  return t_copy_out<T>(E, vals, E->K.vals, E->base->nnz);
+}
+extern "C" int pdlp_get_matrix_values(pdlp_handle h, void* K_vals) {
+  CHECK_HANDLE(h);
+  return DISPATCH(h, t_get_matrix_values, K_vals);
+}
+
+extern "C" int pdlp_primal_objective(pdlp_handle h, double* host_out) {
+  CHECK_HANDLE(h);
+  if (!host_out) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, engine_objective, host_out);
+}
+
+extern "C" int pdlp_solve(pdlp_handle h, const pdlp_solve_options* opts, pdlp_solve_result* host_out,
+                          pdlp_check* host_trace) {
+  CHECK_HANDLE(h);
+  if (!opts || !host_out) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, engine_solve, opts, host_out, host_trace);
+}

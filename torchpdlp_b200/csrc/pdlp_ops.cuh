@@ -1,0 +1,792 @@
+// pdlp_ops.cuh -- fused epilogues ("ops") plugged into stream_kernel, the device
+// scalar block, and the small element-wise kernels around the hot loop.
+//
+// Reference semantics (paths under /root/reference/PDLP):
+//   PrimalOp      primal_dual_hybrid_gradient_step.py:25-27 / :68-77  (x' = clip(x - tau (c - K^T y)))
+//   DualOp        step.py:30-38 / :80-108 (y' = proj(y + sigma (q - K xbar)), step rule)
+//   KktColsOp     helpers.py:75-85,:94   (grad, lambda, objective terms, dual residual)
+//   KktRowsOp     helpers.py:77,:88-91   (q^T y, primal residual)
+//   decide/apply  primal_dual_hybrid_gradient.py:115-177
+#pragma once
+#include <math.h>
+
+#include "stream_spmv.cuh"
+
+namespace pdlp {
+
+template <typename T> struct Pair;
+template <> struct __align__(16) Pair<double> { double a, b; };
+template <> struct __align__(8) Pair<float> { float a, b; };
+
+template <typename T> struct __align__(32) Quad { T v[4]; };
+template <> struct __align__(16) Quad<float> { float v[4]; };
+
+// slots of Quad: the three iterates the restart test evaluates (:121-126)
+enum { IT_CUR = 0, IT_AVG = 1, IT_PREV = 2 };
+
+// raw sums per iterate kept in Scalars::sums[v][*]
+enum { S_PR2 = 0, S_DR2, S_CTX, S_LPOS, S_UNEG, S_QTY, S_PR2U, S_DR2U, S_NSUM };
+
+struct Resid {
+  double pr, dr, gap, prim_obj, adj_dual, kkt, pr_u, dr_u;
+};
+
+struct Scalars {
+  // step state
+  double eta, omega, theta, w_pending, eta_sum;
+  double dx2, dy2, inter, last_weight;
+  double kkt_first, q_norm, c_norm, tol, infeas_tol;
+  long long k;
+  int t, n_restarts, adaptive, primal_update;
+  int infeas_detect, infeas, infeas_k, solved;
+  int stop, m_ineq, pad0, pad1;
+  // restart check
+  double sums[3][S_NSUM];
+  int chk_kind, chk_use_avg, chk_t, chk_solved;
+  long long chk_k;
+  double chk_omega, kkt_cur, kkt_avg, kkt_prev, kkt_first_new;
+  Resid point;
+  double restart_dx2, restart_dy2;
+  // infeasibility detection (enhancements.py:106-161): sums of the latest step
+  double inf_ctdx, inf_bound_viol;                 // c^T dx, #variables failing the bound test (:126-138)
+  double inf_eq2, inf_ineq_viol, inf_qtdy, inf_dy_viol;
+  double inf_dres2, inf_lsum, inf_usum;
+  // scratch reductions: power iteration, Ruiz, norms
+  double scratch[8];
+};
+
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ Pair<double> ldg(const Pair<double>* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return Pair<double>{v.x, v.y};
+}
+__device__ __forceinline__ Pair<float> ldg(const Pair<float>* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return Pair<float>{v.x, v.y};
+}
+
+template <typename T> __device__ __forceinline__ T clampv(T v, T lo, T hi) { return fmin(fmax(v, lo), hi); }
+
+// ---------------------------------------------------------------------------
+// Plain SpMV: out[row] = sum, optional sum of squares -> Scalars::scratch[slot]
+// (power iteration helpers.py:41-51, pdlp_spmv).
+// ---------------------------------------------------------------------------
+template <typename T, bool SUMSQ>
+struct SpmvOp {
+  using value_type = T;
+  static constexpr int NV = 1;
+  static constexpr int NRED = SUMSQ ? 1 : 0;
+  static constexpr int U = 8;
+  const T* in;
+  T* out;
+  Scalars* S;
+  int slot;
+  __device__ bool begin() { return true; }
+  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(in + col); }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
+    T g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(in + col[j]) : T(0);
+#pragma unroll
+    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
+  }
+  __device__ void row(int r, const T (&acc)[1], double (&red)[1]) {
+    out[r] = acc[0];
+    if (SUMSQ) red[0] += (double)acc[0] * (double)acc[0];
+  }
+  __device__ void finalize(const double (&tot)[1]) { S->scratch[slot] = tot[0]; }
+};
+
+// ---------------------------------------------------------------------------
+// K1: rows of K^T (one per variable).  g = c - K^T y; x' = clip(x - tau g, l, u);
+// dx = x' - x; deferred averaging x_sum += w_pending * x; ||dx||^2.
+// ---------------------------------------------------------------------------
+template <typename T, bool SAVE_PREV, bool INFEAS = false>
+struct PrimalOp {
+  using value_type = T;
+  static constexpr int NV = 1;
+  static constexpr int NRED = INFEAS ? 3 : 1;
+  static constexpr int U = 8;
+  const T* y;
+  const T* c;
+  const T* l;
+  const T* u;
+  Pair<T>* xp;       // (x, dx)
+  T* xsum;
+  Quad<T>* X4;
+  Scalars* S;
+  T* kty_old;        // INFEAS: K^T y of the iterate the step started from
+  T tau, wpend, itol;
+  __device__ bool begin() {
+    if (S->stop) return false;
+    tau = (T)(S->eta / S->omega);
+    wpend = (T)S->w_pending;
+    itol = (T)S->infeas_tol;
+    return true;
+  }
+  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(y + col); }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
+    T g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(y + col[j]) : T(0);
+#pragma unroll
+    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
+  }
+  __device__ void row(int j, const T (&acc)[1], double (&red)[NRED]) {
+    const T cj = c[j], lj = l[j], uj = u[j];
+    const T g = cj - acc[0];
+    const T xo = xp[j].a;
+    const T xn = clampv(xo - tau * g, lj, uj);
+    const T dx = xn - xo;
+    xp[j] = Pair<T>{xn, dx};
+    xsum[j] += wpend * xo;
+    if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
+    red[0] += (double)dx * (double)dx;
+    if (INFEAS) {
+      kty_old[j] = acc[0];
+      red[1] += (double)cj * (double)dx;
+      // enhancements.py:132-136
+      const bool ok = (!isinf(lj) && !isinf(uj) && fabs(dx) <= itol) || (uj == (T)INFINITY && cj >= T(0) && dx >= -itol) ||
+                      (lj == -(T)INFINITY && cj <= T(0) && dx <= itol);
+      red[2] += ok ? 0.0 : 1.0;
+    }
+  }
+  __device__ void finalize(const double (&tot)[NRED]) {
+    S->dx2 = tot[0];
+    if (INFEAS) { S->inf_ctdx = tot[1]; S->inf_bound_viol = tot[2]; }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K2: rows of K.  xbar = x' + theta dx gathered as a pair; y' = y + sigma (q - K xbar),
+// projected on rows < m_ineq; dy; deferred averaging; ||dy||^2 and dy^T (K dx); then the
+// step-size rule on the last CTA.
+// ---------------------------------------------------------------------------
+template <typename T, bool SAVE_PREV, bool INFEAS = false>
+struct DualOp {
+  using value_type = T;
+  static constexpr int NV = 2;
+  static constexpr int NRED = INFEAS ? 6 : 2;
+  static constexpr int U = 8;
+  const Pair<T>* xp;
+  const T* q;
+  T* y;
+  T* ysum;
+  Quad<T>* Y4;
+  Scalars* S;
+  T sigma, theta, wpend, itol;
+  int m_ineq;
+  __device__ bool begin() {
+    if (S->stop) return false;
+    sigma = (T)(S->eta * S->omega);
+    theta = (T)S->theta;
+    wpend = (T)S->w_pending;
+    itol = (T)S->infeas_tol;
+    m_ineq = S->m_ineq;
+    return true;
+  }
+  __device__ void fma(T (&acc)[2], T a, int col) const {
+    const Pair<T> p = ldg(xp + col);
+    acc[0] += a * (p.a + theta * p.b);
+    acc[1] += a * p.b;
+  }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[2], const T (&a)[UU], const int (&col)[UU]) const {
+    Pair<T> g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(xp + col[j]) : Pair<T>{T(0), T(0)};
+#pragma unroll
+    for (int j = 0; j < UU; ++j) {
+      acc[0] += a[j] * (g[j].a + theta * g[j].b);
+      acc[1] += a[j] * g[j].b;
+    }
+  }
+  __device__ void row(int i, const T (&acc)[2], double (&red)[NRED]) {
+    const T yo = y[i];
+    const T qi = q[i];
+    T yn = yo + sigma * (qi - acc[0]);
+    if (i < m_ineq) yn = fmax(yn, T(0));
+    const T dy = yn - yo;
+    y[i] = yn;
+    ysum[i] += wpend * yo;
+    if (SAVE_PREV) Y4[i].v[IT_PREV] = yo;
+    red[0] += (double)dy * (double)dy;
+    red[1] += (double)dy * (double)acc[1];
+    if (INFEAS) {
+      const T kdx = acc[1];                                   // (K dx)_i
+      if (i < m_ineq) {
+        red[3] += kdx >= -itol ? 0.0 : 1.0;                   // enhancements.py:119
+        red[5] += dy >= -itol ? 0.0 : 1.0;                    // :147
+      } else {
+        red[2] += (double)kdx * (double)kdx;                  // :116
+      }
+      red[4] += (double)qi * (double)dy;                      // :148
+    }
+  }
+  // step.py:96-115 (adaptive) / :40 (fixed) and primal_dual_hybrid_gradient.py:104-112
+  __device__ void finalize(const double (&tot)[NRED]) {
+    Scalars& s = *S;
+    s.dy2 = tot[0];
+    s.inter = tot[1];
+    const long long k = s.k + 1;
+    s.k = k;
+    const double eta = s.eta, omega = s.omega;
+    double w = eta, next = eta;
+    if (s.adaptive) {
+      const double den = 2.0 * tot[1];
+      double eta_bar, t1;
+      if (den != 0.0) {
+        eta_bar = (omega * s.dx2 + tot[0] / omega) / fabs(den);
+        t1 = (1.0 - pow((double)(k + 1), -0.3)) * eta_bar;
+      } else {
+        eta_bar = INFINITY;
+        t1 = INFINITY;
+      }
+      const double t2 = (1.0 + pow((double)(k + 1), -0.6)) * eta;
+      const double ep = fmin(t1, t2);
+      if (eta <= eta_bar) { w = eta; next = ep; } else { w = ep; next = ep; }
+    }
+    if (INFEAS) {
+      s.inf_eq2 = tot[2]; s.inf_ineq_viol = tot[3]; s.inf_qtdy = tot[4]; s.inf_dy_viol = tot[5];
+      // dual infeasibility test, enhancements.py:116-141 (only from the second iteration on, pdlp :89)
+      if (k > 1 && sqrt(tot[2]) < s.infeas_tol && tot[3] == 0.0 && s.inf_ctdx < s.infeas_tol &&
+          s.inf_bound_viol == 0.0) {
+        s.infeas = 1;
+        s.infeas_k = (int)k;
+        s.stop = 1;
+        s.last_weight = w;
+        return;   // the reference returns before the averaging update (:94-100)
+      }
+    }
+    s.eta_sum += w;
+    s.w_pending = w;
+    s.last_weight = w;
+    s.eta = next;
+    s.t += 1;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Infeasibility, column side (after K2): lam = proj(c - K^T y'), dlam = lam - lam_prev,
+// dual_res = K^T dy - dlam, certificate sums (enhancements.py:106-112,145-159; call site pdlp :90).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct InfeasColsOp {
+  using value_type = T;
+  static constexpr int NV = 1;
+  static constexpr int NRED = 3;
+  static constexpr int U = 8;
+  const T* y;
+  const T* c;
+  const T* l;
+  const T* u;
+  const T* kty_old;
+  T* lam_prev;
+  Scalars* S;
+  __device__ bool begin() { return !S->stop && S->k >= 2; }
+  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(y + col); }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
+    T g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(y + col[j]) : T(0);
+#pragma unroll
+    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
+  }
+  __device__ void row(int j, const T (&acc)[1], double (&red)[3]) {
+    const T lj = l[j], uj = u[j];
+    const bool lo_inf = isinf(lj) && lj < T(0);
+    const bool up_inf = isinf(uj) && uj > T(0);
+    const T g = c[j] - acc[0];
+    T lam;
+    if (lo_inf && up_inf) lam = T(0);
+    else if (lo_inf) lam = fmin(g, T(0));
+    else if (up_inf) lam = fmax(g, T(0));
+    else lam = g;
+    const T dlam = lam - lam_prev[j];
+    lam_prev[j] = lam;                                        // pdlp :101
+    const T dres = (acc[0] - kty_old[j]) - dlam;              // K^T dy - dlam, :145
+    red[0] += (double)dres * (double)dres;
+    if (!isinf(lj) && lj != T(0)) red[1] += (double)lj * (double)fmax(dlam, T(0));    // :112,:154
+    if (!isinf(uj) && uj != T(0)) red[2] += (double)uj * (double)fmax(-dlam, T(0));   // :111,:156
+  }
+  __device__ void finalize(const double (&tot)[3]) {
+    Scalars& s = *S;
+    s.inf_dres2 = tot[0]; s.inf_lsum = tot[1]; s.inf_usum = tot[2];
+    if (sqrt(tot[0]) < s.infeas_tol && s.inf_dy_viol == 0.0) {
+      const double combo = s.inf_qtdy - tot[1] - tot[2];
+      if (combo > -s.infeas_tol) {
+        s.infeas = 2;
+        s.infeas_k = (int)s.k;
+        s.stop = 1;
+        // undo the averaging bookkeeping of this iteration: the reference returns before it (:94-100)
+        s.eta_sum -= s.w_pending;
+        s.w_pending = 0.0;
+        s.t -= 1;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// KKT, column side: rows of K^T, three iterates at once (Y4 gathered).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct KktColsOp {
+  using value_type = T;
+  static constexpr int NV = 3;
+  static constexpr int NRED = 15;   // per iterate: dr2, cTx, lpos, uneg, dr2u
+  static constexpr int U = 4;
+  const Quad<T>* Y4;
+  const Quad<T>* X4;
+  const T* c;
+  const T* l;
+  const T* u;
+  const T* dcol;     // nullptr when unscaled
+  Scalars* S;
+  __device__ bool begin() { return true; }
+  __device__ void fma(T (&acc)[3], T a, int col) const {
+    const Quad<T> g = Y4[col];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) acc[v] += a * g.v[v];
+  }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[3], const T (&a)[UU], const int (&col)[UU]) const {
+    Quad<T> g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) {
+      if (col[j] >= 0) g[j] = Y4[col[j]];
+      else g[j] = Quad<T>{{T(0), T(0), T(0), T(0)}};
+    }
+#pragma unroll
+    for (int j = 0; j < UU; ++j) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) acc[v] += a[j] * g[j].v[v];
+    }
+  }
+  __device__ void row(int j, const T (&acc)[3], double (&red)[15]) {
+    const T cj = c[j], lj = l[j], uj = u[j];
+    const bool lo_inf = isinf(lj) && lj < T(0);
+    const bool up_inf = isinf(uj) && uj > T(0);
+    const T ld = lo_inf ? T(0) : lj;      // l_dual, :14-17
+    const T ud = up_inf ? T(0) : uj;
+    const T inv = dcol ? T(1) / dcol[j] : T(1);
+    const Quad<T> x = X4[j];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const T g = cj - acc[v];
+      T lam;                               // helpers.py:3-39
+      if (lo_inf && up_inf) lam = T(0);
+      else if (lo_inf) lam = fmin(g, T(0));
+      else if (up_inf) lam = fmax(g, T(0));
+      else lam = g;
+      const T d = g - lam;
+      red[5 * v + 0] += (double)d * (double)d;
+      red[5 * v + 1] += (double)cj * (double)x.v[v];
+      red[5 * v + 2] += (double)ld * (double)fmax(lam, T(0));
+      red[5 * v + 3] += (double)ud * (double)fmin(lam, T(0));
+      const T du = d * inv;
+      red[5 * v + 4] += (double)du * (double)du;
+    }
+  }
+  __device__ void finalize(const double (&tot)[15]) {
+    for (int v = 0; v < 3; ++v) {
+      S->sums[v][S_DR2] = tot[5 * v + 0];
+      S->sums[v][S_CTX] = tot[5 * v + 1];
+      S->sums[v][S_LPOS] = tot[5 * v + 2];
+      S->sums[v][S_UNEG] = tot[5 * v + 3];
+      S->sums[v][S_DR2U] = tot[5 * v + 4];
+    }
+    S->w_pending = 0.0;   // the flush kernel folded the pending weight into the sums
+  }
+};
+
+// ---------------------------------------------------------------------------
+// KKT, row side: rows of K, three iterates at once (X4 gathered).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct KktRowsOp {
+  using value_type = T;
+  static constexpr int NV = 3;
+  static constexpr int NRED = 9;    // per iterate: pr2, qTy, pr2u
+  static constexpr int U = 4;
+  const Quad<T>* X4;
+  const Quad<T>* Y4;
+  const T* q;
+  const T* drow;     // nullptr when unscaled
+  Scalars* S;
+  int m_ineq;
+  __device__ bool begin() { m_ineq = S->m_ineq; return true; }
+  __device__ void fma(T (&acc)[3], T a, int col) const {
+    const Quad<T> g = X4[col];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) acc[v] += a * g.v[v];
+  }
+  template <int UU>
+  __device__ void fma_batch(T (&acc)[3], const T (&a)[UU], const int (&col)[UU]) const {
+    Quad<T> g[UU];
+#pragma unroll
+    for (int j = 0; j < UU; ++j) {
+      if (col[j] >= 0) g[j] = X4[col[j]];
+      else g[j] = Quad<T>{{T(0), T(0), T(0), T(0)}};
+    }
+#pragma unroll
+    for (int j = 0; j < UU; ++j) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) acc[v] += a[j] * g[j].v[v];
+    }
+  }
+  __device__ void row(int i, const T (&acc)[3], double (&red)[9]) {
+    const T qi = q[i];
+    const T inv = drow ? T(1) / drow[i] : T(1);
+    const Quad<T> yv = Y4[i];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      T r = acc[v] - qi;                       // helpers.py:88
+      if (i < m_ineq) r = fmin(r, T(0));       // :89
+      red[3 * v + 0] += (double)r * (double)r;
+      red[3 * v + 1] += (double)qi * (double)yv.v[v];
+      const T ru = r * inv;
+      red[3 * v + 2] += (double)ru * (double)ru;
+    }
+  }
+  __device__ void finalize(const double (&tot)[9]) {
+    for (int v = 0; v < 3; ++v) {
+      S->sums[v][S_PR2] = tot[3 * v + 0];
+      S->sums[v][S_QTY] = tot[3 * v + 1];
+      S->sums[v][S_PR2U] = tot[3 * v + 2];
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+__host__ __device__ inline Resid make_resid(const double (&s)[S_NSUM], double omega) {
+  Resid r;
+  r.pr = sqrt(s[S_PR2]);
+  r.dr = sqrt(s[S_DR2]);
+  r.prim_obj = s[S_CTX];
+  r.adj_dual = s[S_QTY] + s[S_LPOS] + s[S_UNEG];     // helpers.py:84
+  r.gap = r.adj_dual - r.prim_obj;                   // :85 (signed)
+  const double w2 = omega * omega;
+  r.kkt = sqrt(w2 * r.pr * r.pr + r.dr * r.dr / w2 + r.gap * r.gap);   // :105
+  r.pr_u = sqrt(s[S_PR2U]);
+  r.dr_u = sqrt(s[S_DR2U]);
+  return r;
+}
+
+// restart criteria, primal_dual_hybrid_gradient.py:121-141
+__global__ void decide_kernel(Scalars* S, int force) {
+  Scalars& s = *S;
+  const Resid rc = make_resid(s.sums[IT_CUR], s.omega);
+  const Resid ra = make_resid(s.sums[IT_AVG], s.omega);
+  const Resid rp = make_resid(s.sums[IT_PREV], s.omega);
+  s.kkt_cur = rc.kkt;
+  s.kkt_avg = ra.kkt;
+  s.kkt_prev = rp.kkt;
+  const double kmin = fmin(rc.kkt, ra.kkt);
+  int kind = 0;
+  int use_avg = rc.kkt >= ra.kkt ? 1 : 0;
+  if (force) {
+    kind = 4;
+    use_avg = 0;
+  } else if (kmin <= 0.2 * s.kkt_first) {
+    kind = 1;
+  } else if (kmin <= 0.8 * s.kkt_first && kmin > rp.kkt) {
+    kind = 2;
+  } else if ((double)s.t >= 0.36 * (double)s.k) {
+    kind = 3;
+  }
+  s.chk_kind = kind;
+  s.chk_use_avg = use_avg;
+  s.chk_t = s.t;
+  s.chk_k = s.k;
+  s.chk_solved = 0;
+  s.point = use_avg ? ra : rc;
+  s.restart_dx2 = 0.0;
+  s.restart_dy2 = 0.0;
+}
+
+// after apply_restart: primal weight (enhancements.py:73-78), KKT_first (:153), termination (:173)
+__global__ void post_restart_kernel(Scalars* S, int scaled) {
+  Scalars& s = *S;
+  if (s.chk_kind == 0) return;
+  s.n_restarts += 1;
+  if (s.primal_update) {
+    const double dxn = sqrt(s.restart_dx2), dyn = sqrt(s.restart_dy2);
+    if (dxn > 0.0 && dyn > 0.0) s.omega = exp(0.5 * log(dyn / dxn) + 0.5 * log(s.omega));
+  }
+  const double w2 = s.omega * s.omega;
+  Resid& p = s.point;
+  p.kkt = sqrt(w2 * p.pr * p.pr + p.dr * p.dr / w2 + p.gap * p.gap);
+  s.kkt_first = p.kkt;
+  s.kkt_first_new = p.kkt;
+  s.chk_omega = s.omega;
+  const double pr = scaled ? p.pr_u : p.pr;
+  const double dr = scaled ? p.dr_u : p.dr;
+  const bool ok = pr <= s.tol * (1.0 + s.q_norm) && dr <= s.tol * (1.0 + s.c_norm) &&
+                  p.gap <= s.tol * (1.0 + fabs(p.prim_obj) + fabs(p.adj_dual));     // helpers.py:125-128
+  s.chk_solved = ok ? 1 : 0;
+  s.solved = ok ? 1 : 0;
+  s.t = 0;
+  s.eta_sum = 0.0;
+  s.w_pending = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// element-wise kernels
+// ---------------------------------------------------------------------------
+// fold the pending weight into the sums and lay out the iterates for the KKT pass (:118-119)
+template <typename T>
+__global__ void flush_kernel(const Pair<T>* xp, const T* y, T* xsum, T* ysum, Quad<T>* X4, Quad<T>* Y4, int n, int m,
+                             const Scalars* S, int have_prev) {
+  const T wp = (T)S->w_pending;
+  const T es = (T)S->eta_sum;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T xo = xp[j].a;
+    const T sm = xsum[j] + wp * xo;
+    xsum[j] = sm;
+    Quad<T> qd = X4[j];
+    qd.v[IT_CUR] = xo;
+    qd.v[IT_AVG] = es > T(0) ? sm / es : xo;
+    if (!have_prev) qd.v[IT_PREV] = xo;
+    qd.v[3] = T(0);
+    X4[j] = qd;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const T yo = y[i];
+    const T sm = ysum[i] + wp * yo;
+    ysum[i] = sm;
+    Quad<T> qd = Y4[i];
+    qd.v[IT_CUR] = yo;
+    qd.v[IT_AVG] = es > T(0) ? sm / es : yo;
+    if (!have_prev) qd.v[IT_PREV] = yo;
+    qd.v[3] = T(0);
+    Y4[i] = qd;
+  }
+}
+
+// restart at the chosen candidate: copy, zero the sums, ||x - x_last_restart||^2 (:58-64,:133,:150)
+template <typename T>
+__global__ void apply_restart_kernel(Pair<T>* xp, T* y, T* xsum, T* ysum, const Quad<T>* X4, const Quad<T>* Y4,
+                                     T* xlast, T* ylast, int n, int m, Scalars* S, double* partials,
+                                     unsigned int* ticket) {
+  if (S->chk_kind == 0) return;
+  const int slot = S->chk_use_avg ? IT_AVG : IT_CUR;
+  const int stride = gridDim.x * blockDim.x;
+  double dx2 = 0.0, dy2 = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T xc = X4[j].v[slot];
+    const T d = xlast[j] - xc;
+    dx2 += (double)d * (double)d;
+    xp[j] = Pair<T>{xc, T(0)};
+    xlast[j] = xc;
+    xsum[j] = T(0);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const T yc = Y4[i].v[slot];
+    const T d = ylast[i] - yc;
+    dy2 += (double)d * (double)d;
+    y[i] = yc;
+    ylast[i] = yc;
+    ysum[i] = T(0);
+  }
+  // fixed-order block + grid reduction
+  __shared__ double sh[2][32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+    dy2 += __shfl_xor_sync(0xffffffffu, dy2, o);
+  }
+  if (lane == 0) { sh[0][warp] = dx2; sh[1][warp] = dy2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (int bl = 0; bl < (int)gridDim.x; ++bl) { a += __ldcg(&partials[2 * bl]); b += __ldcg(&partials[2 * bl + 1]); }
+    S->restart_dx2 = a;
+    S->restart_dy2 = b;
+    *ticket = 0u;
+  }
+}
+
+template <typename T>
+__global__ void set_iterate_kernel(const T* x, const T* y, Pair<T>* xp, T* yy, T* xsum, T* ysum, T* xlast, T* ylast,
+                                   int n, int m) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T v = x ? x[j] : T(0);
+    xp[j] = Pair<T>{v, T(0)};
+    xsum[j] = T(0);
+    xlast[j] = v;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const T v = y ? y[i] : T(0);
+    yy[i] = v;
+    ysum[i] = T(0);
+    ylast[i] = v;
+  }
+}
+
+template <typename T>
+__global__ void get_iterate_kernel(const Pair<T>* xp, const T* yy, T* x, T* y, int n, int m) {
+  const int stride = gridDim.x * blockDim.x;
+  if (x) for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) x[j] = xp[j].a;
+  if (y) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) y[i] = yy[i];
+}
+
+template <typename T>
+__global__ void get_average_kernel(const Pair<T>* xp, const T* yy, const T* xsum, const T* ysum, T* x, T* y, int n,
+                                   int m, const Scalars* S) {
+  const T wp = (T)S->w_pending, es = (T)S->eta_sum;
+  const int stride = gridDim.x * blockDim.x;
+  if (x) for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    x[j] = es > T(0) ? (xsum[j] + wp * xp[j].a) / es : xp[j].a;
+  if (y) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+    y[i] = es > T(0) ? (ysum[i] + wp * yy[i]) / es : yy[i];
+}
+
+// X4[j] = (x, x, x, 0): standalone KKT of caller vectors
+template <typename T>
+__global__ void pack3_kernel(const T* x, Quad<T>* X4, int n) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T v = x[j];
+    X4[j] = Quad<T>{{v, v, v, T(0)}};
+  }
+}
+
+// b = v / sqrt(scratch[slot])   (helpers.py:50)
+template <typename T>
+__global__ void normalize_kernel(const T* v, T* b, int n, const Scalars* S, int slot) {
+  const T nrm = (T)sqrt(S->scratch[slot]);
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) b[j] = v[j] / nrm;
+}
+
+// c^T x of the current iterate -> scratch[slot] (single block, fixed order)
+template <typename T>
+__global__ void objective_kernel(const T* c, const Pair<T>* xp, int n, Scalars* S, int slot) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) a += (double)c[j] * (double)xp[j].a;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    S->scratch[slot] = t;
+  }
+}
+
+// sum of squares of a vector -> scratch[slot] (single block, fixed order)
+template <typename T>
+__global__ void sumsq_kernel(const T* v, int n, Scalars* S, int slot) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) a += (double)v[j] * (double)v[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    S->scratch[slot] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// preconditioning (setup time; enhancements.py:43-71)
+// ---------------------------------------------------------------------------
+// out[row] = max |vals| (MODE 0) or sum |vals| (MODE 1) over the row; one warp per row
+template <typename T, int MODE>
+__global__ void row_absreduce_kernel(const int* rowptr, const T* vals, int rows, T* out) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    T a = T(0);
+    for (int e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) {
+      const T v = fabs(vals[e]);
+      a = MODE == 0 ? fmax(a, v) : a + v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T b = __shfl_xor_sync(0xffffffffu, a, o);
+      a = MODE == 0 ? fmax(a, b) : a + b;
+    }
+    if (lane == 0) out[r] = a;
+  }
+}
+
+// norms <- sqrt(norms), entries < eps -> 1, D /= norms; scratch[slot] = max |1 - norms| (single block)
+template <typename T>
+__global__ void ruiz_fix_kernel(T* norms, T* D, int len, T eps, Scalars* S, int slot) {
+  __shared__ double sh[32];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    T r = sqrt(norms[i]);
+    if (r < eps) r = T(1);
+    norms[i] = r;
+    D[i] = D[i] / r;
+    mx = fmax(mx, fabs(1.0 - (double)r));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, sh[w]);
+    S->scratch[slot] = t;
+  }
+}
+
+template <typename T>
+__global__ void scale_rows_kernel(const int* rowptr, T* vals, int rows, const T* div) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const T d = div[r];
+    for (int e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) vals[e] = vals[e] / d;
+  }
+}
+
+template <typename T>
+__global__ void scale_cols_kernel(const int* colidx, T* vals, int nnz, const T* div) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) vals[e] = vals[e] / div[colidx[e]];
+}
+
+// v = v * s (MODE 0) or v / s (MODE 1), element-wise
+template <typename T, int MODE>
+__global__ void vec_scale_kernel(T* v, const T* s, int len) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) v[i] = MODE == 0 ? v[i] * s[i] : v[i] / s[i];
+}
+
+template <typename T>
+__global__ void fill_kernel(T* v, T val, int len) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) v[i] = val;
+}
+
+}  // namespace pdlp

@@ -1,0 +1,252 @@
+"""Host-side handle around the C-ABI engine (include/pdlp_b200.h).
+
+PyTorch is used here for device memory, streams and format conversion only; every
+PDHG iteration, KKT pass, power-iteration round and scaling pass runs in
+libpdlp_b200.so.  There is no CPU path: constructing an :class:`Engine` without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Check, Residuals, SolveOptions, SolveResult, State, check
+
+STATUS_STRINGS = {
+    0: "Solved",                                   # primal_dual_hybrid_gradient.py:174
+    1: "Unsolved (KKT passes limit exceeded)",     # :51
+    2: "Unsolved (Time limit exceeded)",           # :71
+    3: "PRIMAL_INFEASIBLE",                        # enhancements.py:159
+    4: "DUAL_INFEASIBLE",                          # enhancements.py:141
+}
+RESTART_KINDS = {0: None, 1: "Sufficient", 2: "Necessary", 3: "Artificial", 4: "Limit"}
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("torchpdlp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError(f"torchpdlp_b200 runs on CUDA devices only, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def to_device_csr(K, device: torch.device, dtype: torch.dtype):
+    """(crow int32, col int32, val) of K and of K^T on ``device``, columns sorted
+    inside every row.  Accepts a torch tensor (dense / COO / CSR, any device), a
+    scipy sparse matrix, or a (crow, col, val, shape) tuple."""
+    if isinstance(K, tuple):
+        crow, col, val, shape = K
+        Kc = torch.sparse_csr_tensor(torch.as_tensor(crow, dtype=torch.int64), torch.as_tensor(col, dtype=torch.int64),
+                                     torch.as_tensor(val, dtype=dtype), size=tuple(shape))
+    elif isinstance(K, torch.Tensor):
+        Kc = K
+    else:  # scipy
+        Ks = K.tocsr()
+        Ks.sort_indices()
+        Kc = torch.sparse_csr_tensor(torch.from_numpy(Ks.indptr.astype(np.int64)),
+                                     torch.from_numpy(Ks.indices.astype(np.int64)),
+                                     torch.from_numpy(np.ascontiguousarray(Ks.data)).to(dtype), size=Ks.shape)
+    Kc = Kc.to(device)
+    if Kc.dtype != dtype:
+        Kc = Kc.to(dtype)
+    if Kc.layout == torch.strided:
+        coo = Kc.to_sparse_coo().coalesce()
+    elif Kc.layout == torch.sparse_coo:
+        coo = Kc.coalesce()
+    elif Kc.layout == torch.sparse_csr:
+        coo = Kc.to_sparse_coo().coalesce()
+    else:
+        raise TypeError(f"unsupported K layout {Kc.layout}")
+    m, n = coo.shape
+    rows, cols, vals = coo.indices()[0], coo.indices()[1], coo.values()
+
+    def csr_of(r, c, v, nrows):
+        counts = torch.bincount(r, minlength=nrows)
+        crow = torch.zeros(nrows + 1, dtype=torch.int64, device=device)
+        torch.cumsum(counts, 0, out=crow[1:])
+        return crow.to(torch.int32).contiguous(), c.to(torch.int32).contiguous(), v.contiguous()
+
+    csr = csr_of(rows, cols, vals, m)                     # coalesced COO is sorted by (row, col)
+    order = torch.argsort(cols * m + rows)                # sort by (col, row): stable, unique keys
+    csc = csr_of(cols[order], rows[order], vals[order], n)
+    return (m, n, int(vals.numel())), csr, csc
+
+
+@dataclass
+class SolveOutput:
+    x: torch.Tensor
+    y: torch.Tensor
+    prim_obj: float
+    k: int
+    n: int
+    j: int
+    status: str
+    seconds: float
+    device_ms: float
+    trace: list
+
+
+class Engine:
+    """One LP (c, K, q, m_ineq, l, u) resident on one GPU."""
+
+    def __init__(self, K, m_ineq: int, c, q, l, u, device=None, dtype: Optional[torch.dtype] = None):
+        self.device = _require_cuda(device)
+        self.lib = _lib.lib()
+        if dtype is None:
+            dtype = K.dtype if isinstance(K, torch.Tensor) else torch.float64
+        if dtype not in (torch.float64, torch.float32):
+            raise TypeError("dtype must be float64 or float32")
+        self.dtype = dtype
+        with torch.cuda.device(self.device):
+            (self.m, self.n, self.nnz), csr, csc = to_device_csr(K, self.device, dtype)
+            self.m_ineq = int(m_ineq)
+            vec = lambda v, ln: torch.as_tensor(v, dtype=dtype).reshape(-1).to(self.device).contiguous()
+            c, q, l, u = vec(c, self.n), vec(q, self.m), vec(l, self.n), vec(u, self.n)
+            if c.numel() != self.n or l.numel() != self.n or u.numel() != self.n or q.numel() != self.m:
+                raise ValueError("vector sizes do not match K")
+            self._csr = csr          # kept for matrix() / debugging (structure only is reused)
+            self.stream = torch.cuda.current_stream(self.device)
+            h = C.c_void_p()
+            torch.cuda.synchronize(self.device)
+            check(self.lib.pdlp_create(C.byref(h), 0 if dtype == torch.float64 else 1, self.m, self.n, self.m_ineq,
+                                       self.nnz, csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
+                                       csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), c.data_ptr(),
+                                       q.data_ptr(), l.data_ptr(), u.data_ptr(), self.stream.cuda_stream))
+            self.h = h
+        self.bytes_per_iteration = int(self.lib.pdlp_bytes_per_iteration(self.h))
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pdlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _new(self, length):
+        return torch.empty(length, dtype=self.dtype, device=self.device)
+
+    def _dev(self, v, length):
+        t = torch.as_tensor(v, dtype=self.dtype).reshape(-1).to(self.device).contiguous()
+        if t.numel() != length:
+            raise ValueError(f"expected {length} values, got {t.numel()}")
+        return t
+
+    # -- iterate / scalars ------------------------------------------------
+    def set_iterate(self, x=None, y=None):
+        xd = self._dev(x, self.n) if x is not None else None
+        yd = self._dev(y, self.m) if y is not None else None
+        check(self.lib.pdlp_set_iterate(self.h, xd.data_ptr() if xd is not None else None,
+                                        yd.data_ptr() if yd is not None else None))
+
+    def get_iterate(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        x, y = self._new(self.n), self._new(self.m)
+        check(self.lib.pdlp_get_iterate(self.h, x.data_ptr(), y.data_ptr()))
+        return x, y
+
+    def get_average(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        x, y = self._new(self.n), self._new(self.m)
+        check(self.lib.pdlp_get_average(self.h, x.data_ptr(), y.data_ptr()))
+        return x, y
+
+    def set_step(self, eta: float, omega: float, theta: float = 1.0, adaptive: bool = False):
+        check(self.lib.pdlp_set_step(self.h, float(eta), float(omega), float(theta), int(bool(adaptive))))
+
+    def set_options(self, tol=1e-4, primal_update=False, infeasibility_detect=False, infeas_tol=1e-4):
+        check(self.lib.pdlp_set_options(self.h, float(tol), int(bool(primal_update)),
+                                        int(bool(infeasibility_detect)), float(infeas_tol)))
+
+    def set_counters(self, k: int, t: int = 0):
+        check(self.lib.pdlp_set_counters(self.h, int(k), int(t)))
+
+    def state(self) -> State:
+        s = State()
+        check(self.lib.pdlp_get_state(self.h, C.byref(s)))
+        return s
+
+    # -- hot loop -----------------------------------------------------------
+    def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = True):
+        check(self.lib.pdlp_iterate(self.h, int(n_iters), int(bool(save_previous)), int(bool(use_graph))))
+
+    def restart_check(self, force: bool = False) -> Check:
+        chk = Check()
+        check(self.lib.pdlp_restart_check(self.h, int(bool(force)), C.byref(chk)))
+        return chk
+
+    def kkt(self, x, y, omega: float) -> Residuals:
+        xd, yd = self._dev(x, self.n), self._dev(y, self.m)
+        r = Residuals()
+        check(self.lib.pdlp_kkt(self.h, xd.data_ptr(), yd.data_ptr(), float(omega), C.byref(r)))
+        return r
+
+    def primal_objective(self) -> float:
+        v = C.c_double()
+        check(self.lib.pdlp_primal_objective(self.h, C.byref(v)))
+        return v.value
+
+    # -- setup-time kernels -------------------------------------------------
+    def power_iteration(self, b0, iters: int) -> float:
+        b = self._dev(b0, self.n)
+        sigma = C.c_double()
+        check(self.lib.pdlp_power_iteration(self.h, b.data_ptr(), int(iters), C.byref(sigma)))
+        return sigma.value
+
+    def spmv(self, v, transpose: bool = False) -> torch.Tensor:
+        vin = self._dev(v, self.m if transpose else self.n)
+        out = self._new(self.n if transpose else self.m)
+        check(self.lib.pdlp_spmv(self.h, int(bool(transpose)), vin.data_ptr(), out.data_ptr()))
+        return out
+
+    def ruiz(self, max_iter: int = 20, eps: float = 1e-6) -> int:
+        rounds = C.c_int()
+        check(self.lib.pdlp_ruiz(self.h, int(max_iter), float(eps), C.byref(rounds)))
+        return rounds.value
+
+    def pock_chambolle(self):
+        check(self.lib.pdlp_pock_chambolle(self.h))
+
+    def scaling(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        dr, dc = self._new(self.m), self._new(self.n)
+        check(self.lib.pdlp_get_scaling(self.h, dr.data_ptr(), dc.data_ptr()))
+        return dr, dc
+
+    def set_scaling(self, D_row, D_col):
+        dr, dc = self._dev(D_row, self.m), self._dev(D_col, self.n)
+        check(self.lib.pdlp_set_scaling(self.h, dr.data_ptr(), dc.data_ptr()))
+        torch.cuda.synchronize(self.device)
+
+    def problem(self):
+        c, q, l, u = self._new(self.n), self._new(self.m), self._new(self.n), self._new(self.n)
+        check(self.lib.pdlp_get_problem(self.h, c.data_ptr(), q.data_ptr(), l.data_ptr(), u.data_ptr()))
+        return c, q, l, u
+
+    def matrix(self) -> torch.Tensor:
+        """Current (possibly scaled) K as a torch sparse CSR tensor on the device."""
+        vals = self._new(self.nnz)
+        check(self.lib.pdlp_get_matrix_values(self.h, vals.data_ptr()))
+        return torch.sparse_csr_tensor(self._csr[0].to(torch.int64), self._csr[1].to(torch.int64), vals,
+                                       size=(self.m, self.n))
+
+    # -- whole solve ----------------------------------------------------------
+    def solve(self, max_kkt=100_000, restart_period=40, time_limit=3600.0, time_used=0.0, use_graph=True,
+              max_trace=4096) -> SolveOutput:
+        opts = SolveOptions(int(max_kkt), int(restart_period), int(bool(use_graph)), float(time_limit),
+                            float(time_used), int(max_trace), 0)
+        res = SolveResult()
+        trace = (Check * max(1, max_trace))()
+        check(self.lib.pdlp_solve(self.h, C.byref(opts), C.byref(res), trace))
+        x, y = self.get_iterate()
+        return SolveOutput(x, y, res.prim_obj, int(res.k), int(res.n), int(res.j), STATUS_STRINGS[res.status],
+                           res.seconds, res.device_ms, [Check.from_buffer_copy(trace[i]) for i in range(res.n_trace)])

@@ -1,0 +1,155 @@
+"""Drop-in for torchPDLP's PDLP/primal_dual_hybrid_gradient.py.
+
+``pdlp_algorithm`` keeps the reference signature and 7-tuple return
+(primal_dual_hybrid_gradient.py:7, :181) but runs the restart loop on the B200
+engine: two fused kernels per PDHG iteration, scalars resident on the device, one
+host read-back per restart check.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from . import _cache
+from .engine import RESTART_KINDS, STATUS_STRINGS, Engine
+
+_BOUND = "Unsolved (KKT passes limit exceeded)"
+
+
+def initial_step(engine: Engine, power_iters: int = 100, b0=None):
+    """eta = 0.9 / sigma_max(K) and omega = ||c|| / ||q|| (reference :19-23).  The
+    power iteration starts from torch.randn(n, 1) drawn from the global CPU
+    generator in the engine dtype, as helpers.py:47 does on a CPU device."""
+    if b0 is None:
+        b0 = torch.randn(engine.n, 1, dtype=engine.dtype)
+    sigma = engine.power_iteration(b0, power_iters)
+    st = engine.state()
+    eta = (1.0 / sigma) * 0.9          # torch evaluates `0.9 / tensor` as reciprocal * 0.9
+    omega = st.c_norm / st.q_norm if (st.q_norm > 1e-6 and st.c_norm > 1e-6) else 1.0
+    return eta, omega, sigma
+
+
+def _print_restart(chk, verbose):
+    if verbose:
+        kind = RESTART_KINDS[chk.kind]
+        if kind in ("Sufficient", "Necessary", "Artificial"):
+            which = "Average iterate." if chk.use_average else "Current iterate."
+            print(f"{kind} restart at iteration {chk.t} using the", which)
+
+
+def _print_point(k, chk, q_norm, c_norm, scaled, verbose):
+    if verbose:
+        p = chk.point
+        pr = p.pr_unscaled if scaled else p.pr
+        dr = p.dr_unscaled if scaled else p.dr
+        print(f"[{k}] Primal Obj: {p.prim_obj:.4f}, Adjusted Dual Obj: {p.adj_dual:.4f}, "
+              f"Gap: {p.gap / (1 + abs(p.prim_obj) + abs(p.adj_dual)):.2e}, Prim Res: {pr / (1 + q_norm):.2e}, "
+              f"Dual Res: {dr / (1 + c_norm):.2e}")
+        print("")
+
+
+def run_restart_loop(engine: Engine, max_kkt, restart_period, time_limit, time_used, verbose, scaled, use_graph=True,
+                     t_start=None, infeas=False):
+    """The outer / inner loops of :54-177 on the host, one engine call per block of
+    iterations and one per restart test; counters follow the reference (k per
+    iteration, j: +1 per step, +3 per restart test, +2 per restart)."""
+    t_start = time.time() if t_start is None else t_start
+    st = engine.state()
+    q_norm, c_norm = st.q_norm, st.c_norm
+    k, n, j = int(st.k), 0, 0
+    status = _BOUND
+    prim_obj = float("nan")
+    trace = []
+    while j < max_kkt:
+        t = 0
+        restarted = False
+        timed_out = False
+        while j < max_kkt:
+            if time.time() - t_start + time_used >= time_limit:           # :68-74 (tested per block here)
+                status = "Unsolved (Time limit exceeded)"
+                if verbose:
+                    print("Time limit exceeded")
+                timed_out = True
+                break
+            want = restart_period - (t % restart_period)
+            iters, jj, kk = 0, j, k
+            while iters < want and jj < max_kkt:                           # guard before every iteration (:67)
+                kk += 1
+                jj += 1 + (1 if (infeas and kk > 1) else 0)
+                iters += 1
+            at_check = (t + iters) % restart_period == 0
+            engine.iterate(iters, save_previous=at_check, use_graph=use_graph)
+            if infeas:                                                     # :89-101
+                s2 = engine.state()
+                if s2.infeas:
+                    while k < s2.infeas_k:
+                        k += 1
+                        j += 1 + (1 if k > 1 else 0)
+                    status = STATUS_STRINGS[3 if s2.infeas == 2 else 4]
+                    if verbose:
+                        print(f"[PDLP] {status} detected at iteration {k}")
+                    return engine.primal_objective(), k, n, j, status, trace
+            j, k, t = jj, kk, t + iters
+            if at_check:
+                chk = engine.restart_check(False)
+                j += 3                                                     # :128
+                if chk.kind != 0:
+                    _print_restart(chk, verbose)
+                    restarted = True
+                    break
+        if timed_out:
+            break
+        if not restarted:
+            chk = engine.restart_check(True)                               # loop left through the guard (:148)
+        n += 1
+        j += 2                                                             # :154, :165
+        prim_obj = chk.point.prim_obj
+        trace.append(chk)
+        _print_point(k, chk, q_norm, c_norm, scaled, verbose)
+        if chk.solved:                                                     # :173-177
+            status = "Solved"
+            if verbose:
+                print(f"Converged at iteration {k} restart loop {n}")
+            break
+    return prim_obj, k, n, j, status, trace
+
+
+def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, verbose=True, restart_period=40,
+                   precondition=False, primal_update=False, adaptive=False, data_precond=None,
+                   infeasibility_detect=False, infeas_tol=1e-4, time_limit=3600, time_used=0, x_init=None,
+                   y_init=None, power_iters=100, b0=None, use_graph=True, return_info=False):
+    """Same call and return as the reference (:7, :181):
+    ``(x, prim_obj, k, n, j, status, total_time)`` with ``x`` an (n, 1) tensor on the
+    GPU (in the scaled space when preconditioned, like the reference).  Extra keyword
+    arguments (power_iters, b0, use_graph, return_info) have reference-compatible
+    defaults."""
+    t_start = time.time()
+    engine = _cache.engine_for(K, m_ineq, c, q, l, u, device)
+    scaled = bool(precondition)
+    if precondition and data_precond is not None:
+        D_col, D_row = data_precond[0], data_precond[1]
+        engine.set_scaling(D_row, D_col)
+    eta, omega, sigma = initial_step(engine, power_iters, b0)
+    if x_init is not None and y_init is not None:                          # :31-33
+        engine.set_iterate(x_init, y_init)
+    else:
+        engine.set_iterate(None, None)
+    engine.set_counters(0, 0)
+    engine.set_step(eta, omega, 1.0, adaptive)
+    engine.set_options(tol, primal_update, infeasibility_detect, infeas_tol)
+    if verbose:
+        prim_obj, k, n, j, status, trace = run_restart_loop(engine, max_kkt, restart_period, time_limit, time_used,
+                                                            verbose, scaled, use_graph, t_start,
+                                                            infeas=bool(infeasibility_detect))
+    else:
+        out = engine.solve(max_kkt, restart_period, time_limit, time_used + (time.time() - t_start), use_graph)
+        prim_obj, k, n, j, status, trace = out.prim_obj, out.k, out.n, out.j, out.status, out.trace
+    x, y = engine.get_iterate()
+    torch.cuda.synchronize(engine.device)
+    total = time.time() - t_start + time_used
+    if return_info:
+        info = {"y": y.reshape(-1, 1), "trace": trace, "sigma_max": sigma, "engine": engine,
+                "bytes_per_iteration": engine.bytes_per_iteration}
+        return x.reshape(-1, 1), prim_obj, k, n, j, status, total, info
+    return x.reshape(-1, 1), prim_obj, k, n, j, status, total
