@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libpdlp_b200.so")
+LIB_PATH = os.environ.get("PDLP_B200_LIB") or os.path.join(HERE, "libpdlp_b200.so")   # env: developer sweeps only
 SOURCES = [os.path.join(HERE, "csrc", "pdlp_b200.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "stream_spmv.cuh"), os.path.join(HERE, "csrc", "pdlp_ops.cuh"),
            os.path.join(ROOT, "include", "pdlp_b200.h")]

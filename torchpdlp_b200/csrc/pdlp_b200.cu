@@ -41,18 +41,18 @@ struct HostPlan {
   int grid = 0;
 };
 
-static int floor_pow2(int v) {
+static int ceil_pow2(int v) {
   int p = 1;
-  while (p * 2 <= v) p *= 2;
+  while (p < v) p *= 2;
   return p;
 }
 
-// Greedy row packing: a chunk takes rows while nonzeros <= max_nnz and rows <= max_rows; a row longer than
-// max_nnz becomes a "long" chunk streamed from global memory by the whole CTA.  threads-per-row (power of two)
-// is chosen so that one pass of the CTA's NCONS lanes covers the chunk; when doubling it only costs a modest
-// truncation of the chunk, rows are dropped to make every lane busy.
-static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz, int max_rows, int ncons,
-                           int nwarps, int max_grid, double row_cost_nnz) {
+// Greedy row packing.  A chunk is a run of rows whose nonzeros fit one shared-memory stage.  The CTA's NCONS
+// consumer lanes cover it in ONE pass: threads-per-row tpr (a power of two) is sized so that a row of average
+// length needs a single batch of U gathers per lane, and the chunk takes NCONS / tpr rows.  A row longer than a
+// stage becomes a "long" chunk streamed from global memory by the whole CTA.
+static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz, int max_rows, int ncons, int U,
+                           int max_grid, double row_cost_nnz) {
   HostPlan P;
   int r = 0;
   while (r < rows) {
@@ -63,31 +63,21 @@ static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz
       ++r;
       continue;
     }
+    // look ahead over up to ncons rows to estimate the local row length
+    const int look = std::min(rows, r + ncons);
+    int la = r, lnnz = 0;
+    while (la < look && (rowptr[la + 1] - rowptr[la]) <= max_nnz) { lnnz += rowptr[la + 1] - rowptr[la]; ++la; }
+    const double avg = la > r ? (double)lnnz / (la - r) : 1.0;
+    int tpr = std::min(32, ceil_pow2(std::max(1, (int)((avg * 1.15 + U - 1) / U))));
+    int want_rows = std::max(1, ncons / tpr);
     int e = r, nnz = 0;
-    while (e < rows && (e - r) < max_rows) {
+    while (e < rows && (e - r) < max_rows && (e - r) < want_rows) {
       const int len = rowptr[e + 1] - rowptr[e];
       if (len > max_nnz || nnz + len > max_nnz) break;
       nnz += len;
       ++e;
     }
-    int nr = e - r;
-    int tpr;
-    if (nr >= ncons) {
-      tpr = 1;
-      nr = (nr / ncons) * ncons;
-    } else {
-      tpr = std::min(32, floor_pow2(ncons / nr));
-      if (tpr < 32) {
-        const int nr_b = ncons / (2 * tpr);
-        if (nr_b * 3 >= nr * 2) {   // keep >= 2/3 of the rows and fill every lane
-          tpr *= 2;
-          nr = nr_b;
-        }
-      }
-      // rows are dealt to warps in equal slices; keep the slice a multiple of the groups per warp
-      (void)nwarps;
-    }
-    e = r + nr;
+    const int nr = e - r;     // >= 1: the first row fits
     int tl = 0;
     while ((1 << tl) < tpr) ++tl;
     Chunk c{r, rowptr[r], rowptr[e], (uint32_t)nr | ((uint32_t)tl << 16)};
@@ -217,7 +207,7 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   for (int r = 0; r < rows; ++r)
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   using Cfg = StreamCfg<T>;
-  HostPlan P = build_plan(h_rowptr, rows, Cfg::MAX_CHUNK_NNZ, Cfg::MAX_CHUNK_ROWS, Cfg::NCONS, Cfg::NWARPS,
+  HostPlan P = build_plan(h_rowptr, rows, Cfg::MAX_CHUNK_NNZ, Cfg::MAX_CHUNK_ROWS, Cfg::NCONS, Cfg::U,
                           E->base->sms * E->base->ctas_per_sm, row_cost_nnz);
   A.grid = P.grid;
   A.nchunks = (int)P.chunks.size();
@@ -250,6 +240,13 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   cudaStream_t st = B->stream;
   // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
   const double per_nnz = sizeof(T) + 4.0;
+  {
+    using Rep = DualOp<T, false, false>;
+    CU(cudaFuncSetAttribute(stream_kernel<Rep>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::SMEM_BYTES));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel<Rep>, StreamCfg<T>::NT, StreamCfg<T>::SMEM_BYTES));
+    B->ctas_per_sm = std::max(1, occ);
+  }
   int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals, 5.0 * sizeof(T) / per_nnz);
   if (rc) return rc;
   rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals, 8.0 * sizeof(T) / per_nnz);

@@ -68,6 +68,8 @@ __device__ __forceinline__ Pair<float> ldg(const Pair<float>* p) {
 
 template <typename T> __device__ __forceinline__ T clampv(T v, T lo, T hi) { return fmin(fmax(v, lo), hi); }
 
+struct NoCtx {};
+
 // ---------------------------------------------------------------------------
 // Plain SpMV: out[row] = sum, optional sum of squares -> Scalars::scratch[slot]
 // (power iteration helpers.py:41-51, pdlp_spmv).
@@ -75,24 +77,20 @@ template <typename T> __device__ __forceinline__ T clampv(T v, T lo, T hi) { ret
 template <typename T, bool SUMSQ>
 struct SpmvOp {
   using value_type = T;
+  using Gather = T;
+  using Ctx = NoCtx;
   static constexpr int NV = 1;
   static constexpr int NRED = SUMSQ ? 1 : 0;
-  static constexpr int U = 8;
+  static constexpr int UDIV = 1;
   const T* in;
   T* out;
   Scalars* S;
   int slot;
   __device__ bool begin() { return true; }
-  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(in + col); }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
-    T g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(in + col[j]) : T(0);
-#pragma unroll
-    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
-  }
-  __device__ void row(int r, const T (&acc)[1], double (&red)[1]) {
+  __device__ T gather(int col) const { return ldg(in + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int) const { return Ctx{}; }
+  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&red)[1]) {
     out[r] = acc[0];
     if (SUMSQ) red[0] += (double)acc[0] * (double)acc[0];
   }
@@ -106,9 +104,11 @@ struct SpmvOp {
 template <typename T, bool SAVE_PREV, bool INFEAS = false>
 struct PrimalOp {
   using value_type = T;
+  using Gather = T;
+  struct Ctx { T c, l, u, xo, xs; };
   static constexpr int NV = 1;
   static constexpr int NRED = INFEAS ? 3 : 1;
-  static constexpr int U = 8;
+  static constexpr int UDIV = 1;
   const T* y;
   const T* c;
   const T* l;
@@ -126,31 +126,24 @@ struct PrimalOp {
     itol = (T)S->infeas_tol;
     return true;
   }
-  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(y + col); }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
-    T g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(y + col[j]) : T(0);
-#pragma unroll
-    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
-  }
-  __device__ void row(int j, const T (&acc)[1], double (&red)[NRED]) {
-    const T cj = c[j], lj = l[j], uj = u[j];
-    const T g = cj - acc[0];
-    const T xo = xp[j].a;
-    const T xn = clampv(xo - tau * g, lj, uj);
-    const T dx = xn - xo;
+  __device__ T gather(int col) const { return ldg(y + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], xp[j].a, xsum[j]}; }
+  __device__ void row_finish(int j, const Ctx& k, const T (&acc)[1], double (&red)[NRED]) {
+    const T g = k.c - acc[0];
+    const T xn = clampv(k.xo - tau * g, k.l, k.u);
+    const T dx = xn - k.xo;
     xp[j] = Pair<T>{xn, dx};
-    xsum[j] += wpend * xo;
-    if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
+    xsum[j] = k.xs + wpend * k.xo;
+    if (SAVE_PREV) X4[j].v[IT_PREV] = k.xo;
     red[0] += (double)dx * (double)dx;
     if (INFEAS) {
       kty_old[j] = acc[0];
-      red[1] += (double)cj * (double)dx;
+      red[1] += (double)k.c * (double)dx;
       // enhancements.py:132-136
-      const bool ok = (!isinf(lj) && !isinf(uj) && fabs(dx) <= itol) || (uj == (T)INFINITY && cj >= T(0) && dx >= -itol) ||
-                      (lj == -(T)INFINITY && cj <= T(0) && dx <= itol);
+      const bool ok = (!isinf(k.l) && !isinf(k.u) && fabs(dx) <= itol) ||
+                      (k.u == (T)INFINITY && k.c >= T(0) && dx >= -itol) ||
+                      (k.l == -(T)INFINITY && k.c <= T(0) && dx <= itol);
       red[2] += ok ? 0.0 : 1.0;
     }
   }
@@ -168,9 +161,11 @@ struct PrimalOp {
 template <typename T, bool SAVE_PREV, bool INFEAS = false>
 struct DualOp {
   using value_type = T;
+  using Gather = Pair<T>;
+  struct Ctx { T yo, q, ys; };
   static constexpr int NV = 2;
   static constexpr int NRED = INFEAS ? 6 : 2;
-  static constexpr int U = 8;
+  static constexpr int UDIV = 1;
   const Pair<T>* xp;
   const T* q;
   T* y;
@@ -188,31 +183,19 @@ struct DualOp {
     m_ineq = S->m_ineq;
     return true;
   }
-  __device__ void fma(T (&acc)[2], T a, int col) const {
-    const Pair<T> p = ldg(xp + col);
+  __device__ Pair<T> gather(int col) const { return ldg(xp + col); }
+  __device__ void mac(T (&acc)[2], T a, const Pair<T>& p) const {
     acc[0] += a * (p.a + theta * p.b);
     acc[1] += a * p.b;
   }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[2], const T (&a)[UU], const int (&col)[UU]) const {
-    Pair<T> g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(xp + col[j]) : Pair<T>{T(0), T(0)};
-#pragma unroll
-    for (int j = 0; j < UU; ++j) {
-      acc[0] += a[j] * (g[j].a + theta * g[j].b);
-      acc[1] += a[j] * g[j].b;
-    }
-  }
-  __device__ void row(int i, const T (&acc)[2], double (&red)[NRED]) {
-    const T yo = y[i];
-    const T qi = q[i];
-    T yn = yo + sigma * (qi - acc[0]);
+  __device__ Ctx row_load(int i) const { return Ctx{y[i], q[i], ysum[i]}; }
+  __device__ void row_finish(int i, const Ctx& k, const T (&acc)[2], double (&red)[NRED]) {
+    T yn = k.yo + sigma * (k.q - acc[0]);
     if (i < m_ineq) yn = fmax(yn, T(0));
-    const T dy = yn - yo;
+    const T dy = yn - k.yo;
     y[i] = yn;
-    ysum[i] += wpend * yo;
-    if (SAVE_PREV) Y4[i].v[IT_PREV] = yo;
+    ysum[i] = k.ys + wpend * k.yo;
+    if (SAVE_PREV) Y4[i].v[IT_PREV] = k.yo;
     red[0] += (double)dy * (double)dy;
     red[1] += (double)dy * (double)acc[1];
     if (INFEAS) {
@@ -223,7 +206,7 @@ struct DualOp {
       } else {
         red[2] += (double)kdx * (double)kdx;                  // :116
       }
-      red[4] += (double)qi * (double)dy;                      // :148
+      red[4] += (double)k.q * (double)dy;                     // :148
     }
   }
   // step.py:96-115 (adaptive) / :40 (fixed) and primal_dual_hybrid_gradient.py:104-112
@@ -276,9 +259,11 @@ struct DualOp {
 template <typename T>
 struct InfeasColsOp {
   using value_type = T;
+  using Gather = T;
+  struct Ctx { T c, l, u, kty, lamp; };
   static constexpr int NV = 1;
   static constexpr int NRED = 3;
-  static constexpr int U = 8;
+  static constexpr int UDIV = 1;
   const T* y;
   const T* c;
   const T* l;
@@ -287,31 +272,24 @@ struct InfeasColsOp {
   T* lam_prev;
   Scalars* S;
   __device__ bool begin() { return !S->stop && S->k >= 2; }
-  __device__ void fma(T (&acc)[1], T a, int col) const { acc[0] += a * ldg(y + col); }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[1], const T (&a)[UU], const int (&col)[UU]) const {
-    T g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) g[j] = col[j] >= 0 ? ldg(y + col[j]) : T(0);
-#pragma unroll
-    for (int j = 0; j < UU; ++j) acc[0] += a[j] * g[j];
-  }
-  __device__ void row(int j, const T (&acc)[1], double (&red)[3]) {
-    const T lj = l[j], uj = u[j];
-    const bool lo_inf = isinf(lj) && lj < T(0);
-    const bool up_inf = isinf(uj) && uj > T(0);
-    const T g = c[j] - acc[0];
+  __device__ T gather(int col) const { return ldg(y + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], kty_old[j], lam_prev[j]}; }
+  __device__ void row_finish(int j, const Ctx& k, const T (&acc)[1], double (&red)[3]) {
+    const bool lo_inf = isinf(k.l) && k.l < T(0);
+    const bool up_inf = isinf(k.u) && k.u > T(0);
+    const T g = k.c - acc[0];
     T lam;
     if (lo_inf && up_inf) lam = T(0);
     else if (lo_inf) lam = fmin(g, T(0));
     else if (up_inf) lam = fmax(g, T(0));
     else lam = g;
-    const T dlam = lam - lam_prev[j];
+    const T dlam = lam - k.lamp;
     lam_prev[j] = lam;                                        // pdlp :101
-    const T dres = (acc[0] - kty_old[j]) - dlam;              // K^T dy - dlam, :145
+    const T dres = (acc[0] - k.kty) - dlam;                   // K^T dy - dlam, :145
     red[0] += (double)dres * (double)dres;
-    if (!isinf(lj) && lj != T(0)) red[1] += (double)lj * (double)fmax(dlam, T(0));    // :112,:154
-    if (!isinf(uj) && uj != T(0)) red[2] += (double)uj * (double)fmax(-dlam, T(0));   // :111,:156
+    if (!isinf(k.l) && k.l != T(0)) red[1] += (double)k.l * (double)fmax(dlam, T(0));    // :112,:154
+    if (!isinf(k.u) && k.u != T(0)) red[2] += (double)k.u * (double)fmax(-dlam, T(0));   // :111,:156
   }
   __device__ void finalize(const double (&tot)[3]) {
     Scalars& s = *S;
@@ -337,9 +315,11 @@ struct InfeasColsOp {
 template <typename T>
 struct KktColsOp {
   using value_type = T;
+  using Gather = Quad<T>;
+  struct Ctx { T c, l, u, inv; Quad<T> x; };
   static constexpr int NV = 3;
   static constexpr int NRED = 15;   // per iterate: dr2, cTx, lpos, uneg, dr2u
-  static constexpr int U = 4;
+  static constexpr int UDIV = 2;
   const Quad<T>* Y4;
   const Quad<T>* X4;
   const T* c;
@@ -348,36 +328,20 @@ struct KktColsOp {
   const T* dcol;     // nullptr when unscaled
   Scalars* S;
   __device__ bool begin() { return true; }
-  __device__ void fma(T (&acc)[3], T a, int col) const {
-    const Quad<T> g = Y4[col];
+  __device__ Quad<T> gather(int col) const { return Y4[col]; }
+  __device__ void mac(T (&acc)[3], T a, const Quad<T>& g) const {
 #pragma unroll
     for (int v = 0; v < 3; ++v) acc[v] += a * g.v[v];
   }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[3], const T (&a)[UU], const int (&col)[UU]) const {
-    Quad<T> g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) {
-      if (col[j] >= 0) g[j] = Y4[col[j]];
-      else g[j] = Quad<T>{{T(0), T(0), T(0), T(0)}};
-    }
-#pragma unroll
-    for (int j = 0; j < UU; ++j) {
-#pragma unroll
-      for (int v = 0; v < 3; ++v) acc[v] += a[j] * g[j].v[v];
-    }
-  }
-  __device__ void row(int j, const T (&acc)[3], double (&red)[15]) {
-    const T cj = c[j], lj = l[j], uj = u[j];
-    const bool lo_inf = isinf(lj) && lj < T(0);
-    const bool up_inf = isinf(uj) && uj > T(0);
-    const T ld = lo_inf ? T(0) : lj;      // l_dual, :14-17
-    const T ud = up_inf ? T(0) : uj;
-    const T inv = dcol ? T(1) / dcol[j] : T(1);
-    const Quad<T> x = X4[j];
+  __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], dcol ? T(1) / dcol[j] : T(1), X4[j]}; }
+  __device__ void row_finish(int, const Ctx& k, const T (&acc)[3], double (&red)[15]) {
+    const bool lo_inf = isinf(k.l) && k.l < T(0);
+    const bool up_inf = isinf(k.u) && k.u > T(0);
+    const T ld = lo_inf ? T(0) : k.l;      // l_dual, :14-17
+    const T ud = up_inf ? T(0) : k.u;
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-      const T g = cj - acc[v];
+      const T g = k.c - acc[v];
       T lam;                               // helpers.py:3-39
       if (lo_inf && up_inf) lam = T(0);
       else if (lo_inf) lam = fmin(g, T(0));
@@ -385,10 +349,10 @@ struct KktColsOp {
       else lam = g;
       const T d = g - lam;
       red[5 * v + 0] += (double)d * (double)d;
-      red[5 * v + 1] += (double)cj * (double)x.v[v];
+      red[5 * v + 1] += (double)k.c * (double)k.x.v[v];
       red[5 * v + 2] += (double)ld * (double)fmax(lam, T(0));
       red[5 * v + 3] += (double)ud * (double)fmin(lam, T(0));
-      const T du = d * inv;
+      const T du = d * k.inv;
       red[5 * v + 4] += (double)du * (double)du;
     }
   }
@@ -410,9 +374,11 @@ struct KktColsOp {
 template <typename T>
 struct KktRowsOp {
   using value_type = T;
+  using Gather = Quad<T>;
+  struct Ctx { T q, inv; Quad<T> y; };
   static constexpr int NV = 3;
   static constexpr int NRED = 9;    // per iterate: pr2, qTy, pr2u
-  static constexpr int U = 4;
+  static constexpr int UDIV = 2;
   const Quad<T>* X4;
   const Quad<T>* Y4;
   const T* q;
@@ -420,36 +386,20 @@ struct KktRowsOp {
   Scalars* S;
   int m_ineq;
   __device__ bool begin() { m_ineq = S->m_ineq; return true; }
-  __device__ void fma(T (&acc)[3], T a, int col) const {
-    const Quad<T> g = X4[col];
+  __device__ Quad<T> gather(int col) const { return X4[col]; }
+  __device__ void mac(T (&acc)[3], T a, const Quad<T>& g) const {
 #pragma unroll
     for (int v = 0; v < 3; ++v) acc[v] += a * g.v[v];
   }
-  template <int UU>
-  __device__ void fma_batch(T (&acc)[3], const T (&a)[UU], const int (&col)[UU]) const {
-    Quad<T> g[UU];
-#pragma unroll
-    for (int j = 0; j < UU; ++j) {
-      if (col[j] >= 0) g[j] = X4[col[j]];
-      else g[j] = Quad<T>{{T(0), T(0), T(0), T(0)}};
-    }
-#pragma unroll
-    for (int j = 0; j < UU; ++j) {
-#pragma unroll
-      for (int v = 0; v < 3; ++v) acc[v] += a[j] * g[j].v[v];
-    }
-  }
-  __device__ void row(int i, const T (&acc)[3], double (&red)[9]) {
-    const T qi = q[i];
-    const T inv = drow ? T(1) / drow[i] : T(1);
-    const Quad<T> yv = Y4[i];
+  __device__ Ctx row_load(int i) const { return Ctx{q[i], drow ? T(1) / drow[i] : T(1), Y4[i]}; }
+  __device__ void row_finish(int i, const Ctx& k, const T (&acc)[3], double (&red)[9]) {
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-      T r = acc[v] - qi;                       // helpers.py:88
+      T r = acc[v] - k.q;                      // helpers.py:88
       if (i < m_ineq) r = fmin(r, T(0));       // :89
       red[3 * v + 0] += (double)r * (double)r;
-      red[3 * v + 1] += (double)qi * (double)yv.v[v];
-      const T ru = r * inv;
+      red[3 * v + 1] += (double)k.q * (double)k.y.v[v];
+      const T ru = r * k.inv;
       red[3 * v + 2] += (double)ru * (double)ru;
     }
   }

@@ -48,14 +48,35 @@ constexpr int MAX_RED = 24;
 // ---------------------------------------------------------------------------
 // kernel configuration
 // ---------------------------------------------------------------------------
+#ifndef PDLP_NWARPS
+#define PDLP_NWARPS 7
+#endif
+#ifndef PDLP_CAP
+#define PDLP_CAP 1024
+#endif
+#ifndef PDLP_RCAP
+#define PDLP_RCAP 288
+#endif
+#ifndef PDLP_STAGES
+#define PDLP_STAGES 6
+#endif
+#ifndef PDLP_MINB
+#define PDLP_MINB 2
+#endif
+#ifndef PDLP_U
+#define PDLP_U 4
+#endif
+
 template <typename T>
 struct StreamCfg {
-  static constexpr int NWARPS = 8;                 // consumer warps
+  static constexpr int NWARPS = PDLP_NWARPS;       // consumer warps
   static constexpr int NCONS = NWARPS * 32;
   static constexpr int NT = NCONS + 32;            // + producer warp
-  static constexpr int CAP = 2048;                 // nonzeros per stage (incl. alignment slack)
-  static constexpr int RCAP = 256;                 // rows per stage
-  static constexpr int STAGES = 4;
+  static constexpr int CAP = PDLP_CAP;             // nonzeros per stage (incl. alignment slack)
+  static constexpr int RCAP = PDLP_RCAP;           // rows per stage
+  static constexpr int STAGES = PDLP_STAGES;
+  static constexpr int MINB = PDLP_MINB;           // CTAs per SM the register budget is sized for
+  static constexpr int U = PDLP_U;                 // gathers in flight per lane and batch
   static constexpr int DESC_OFF = 0;
   static constexpr int RPTR_OFF = 128;
   static constexpr int COLS_OFF = RPTR_OFF + ((RCAP + 8) * 4 + 127) / 128 * 128;
@@ -65,6 +86,13 @@ struct StreamCfg {
   static constexpr int MAX_CHUNK_NNZ = CAP - 8;
   static constexpr int MAX_CHUNK_ROWS = RCAP - 8;
 };
+
+// developer experiments (never defined in product builds): isolate pipeline components when timing
+#ifdef PDLP_DBG_NOGATHER
+#define PDLP_COL(c) ((c) & 0)
+#else
+#define PDLP_COL(c) (c)
+#endif
 
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D bulk async copy (TMA)
@@ -116,26 +144,40 @@ __device__ __forceinline__ T shfl_xor_t(T v, int mask) {
 
 // ---------------------------------------------------------------------------
 // The kernel.  Op contract:
+//   using value_type = T;   using Gather = ...;   using Ctx = ...;
 //   static constexpr int NV;      number of accumulators per row
 //   static constexpr int NRED;    number of grid-wide reductions (<= MAX_RED; 0 = none)
-//   static constexpr int U;       gathers kept in flight per lane
-//   using value_type = T;
-//   __device__ bool begin();                       called by every thread first; false -> whole grid exits
-//   __device__ void fma(T (&acc)[NV], T a, int col) const;   acc += a * operand[col]
-//   template <int U> __device__ void fma_batch(T (&acc)[NV], const T (&a)[U], const int (&col)[U]) const;
-//                                                  same for U entries (col < 0 = padding): all gathers first
-//   __device__ void row(int row, const T (&acc)[NV], double (&red)[max(NRED,1)]);   fused epilogue of one row
-//   __device__ void finalize(const double (&tot)[max(NRED,1)]);     one thread of the last CTA
+//   static constexpr int UDIV;    divides the per-lane gather batch (wide Gather types keep registers in check)
+//   __device__ bool begin();                         called by every thread first; false -> whole grid exits
+//   __device__ Gather gather(int col) const;         operand[col] through the read-only path
+//   __device__ void mac(T (&acc)[NV], T a, const Gather& g) const;     acc += a * g
+//   __device__ Ctx row_load(int row) const;          issue the loads the row's epilogue needs (no use yet)
+//   __device__ void row_finish(int row, const Ctx&, const T (&acc)[NV], double (&red)[max(NRED,1)]);
+//   __device__ void finalize(const double (&tot)[max(NRED,1)]);        one thread of the last CTA
+//
+// Consumer warps are software-pipelined over chunks: the gathers and the epilogue operands of chunk i+1 are in
+// flight while chunk i is multiplied, reduced (sub-warp shuffles, fixed order) and finished, so every warp keeps
+// two chunks' worth of L2 gathers outstanding.
 // ---------------------------------------------------------------------------
 template <class Op>
-__global__ void __launch_bounds__(StreamCfg<typename Op::value_type>::NT, 2)
+struct Work {
+  typename Op::Gather g[StreamCfg<typename Op::value_type>::U / Op::UDIV];
+  typename Op::Ctx ctx;
+  int row;     // global row of this lane's group in round 0
+  int i0;      // stage index of the lane's first element
+  int e;       // stage index one past the row's last element
+  bool valid;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(StreamCfg<typename Op::value_type>::NT, StreamCfg<typename Op::value_type>::MINB)
 stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
   using T = typename Op::value_type;
   using Cfg = StreamCfg<T>;
   constexpr int NV = Op::NV;
   constexpr int NRED = Op::NRED;
   constexpr int NR = NRED > 0 ? NRED : 1;
-  constexpr int U = Op::U;   // gathers in flight per lane
+  constexpr int U = Cfg::U / Op::UDIV > 0 ? Cfg::U / Op::UDIV : 1;   // gathers in flight per lane and batch
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[Cfg::STAGES];
@@ -168,13 +210,15 @@ stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
   if (warp == Cfg::NWARPS) {
     // ------------------------------ producer ------------------------------
     if (lane == 0) {
+      Chunk next = cb < ce ? A.chunks[cb] : Chunk{0, 0, 0, 0};
       for (int ci = cb; ci < ce; ++ci) {
         const int it = ci - cb;
         const int s = it % Cfg::STAGES;
         const int use = it / Cfg::STAGES;
+        const Chunk ch = next;
+        if (ci + 1 < ce) next = A.chunks[ci + 1];   // hide the descriptor latency behind the wait below
         if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
         unsigned char* st = smem + (size_t)s * Cfg::STAGE_BYTES;
-        const Chunk ch = A.chunks[ci];
         uint32_t bytes = 16;
         const bool is_long = (ch.meta & CHUNK_LONG) != 0;
         const int nrows = ch.meta & 0xffff;
@@ -200,11 +244,49 @@ stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
     __syncwarp();
   } else {
     // ------------------------------ consumers ------------------------------
-    for (int ci = cb; ci < ce; ++ci) {
+    // issue(): wait for the chunk, start this lane's first batch of gathers and the epilogue operand loads
+    auto issue = [&](int ci, Work<Op>& w) {
       const int it = ci - cb;
       const int s = it % Cfg::STAGES;
-      const int use = it / Cfg::STAGES;
-      mbar_wait(&full_bar[s], use & 1);
+      mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
+      const unsigned char* st = smem + (size_t)s * Cfg::STAGE_BYTES;
+      const Chunk ch = *reinterpret_cast<const Chunk*>(st + Cfg::DESC_OFF);
+      w.valid = false;
+      w.i0 = 0;
+      w.e = 0;
+      w.row = 0;
+      if (ch.meta & CHUNK_LONG) return;
+      const int* rptr = reinterpret_cast<const int*>(st + Cfg::RPTR_OFF);
+      const int* cols = reinterpret_cast<const int*>(st + Cfg::COLS_OFF);
+      const int nrows = ch.meta & 0xffff;
+      const int tl = (ch.meta >> 16) & 0xf;
+      const int tpr = 1 << tl;
+      const int rpw = (nrows + Cfg::NWARPS - 1) / Cfg::NWARPS;
+      const int rw1 = min(nrows, warp * rpw + rpw);
+      const int r = warp * rpw + (lane >> tl);
+      const int li = lane & (tpr - 1);
+      if (r < rw1) {
+        const int roff = ch.row_begin - (ch.row_begin & ~3);
+        const int ebase = ch.nnz_begin & ~3;
+        w.valid = true;
+        w.row = ch.row_begin + r;
+        w.i0 = rptr[roff + r] - ebase + li;
+        w.e = rptr[roff + r + 1] - ebase;
+#ifndef PDLP_DBG_NOEPI
+        if (li == 0) w.ctx = op.row_load(w.row);
+#endif
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int idx = w.i0 + j * tpr;
+        if (idx < w.e) w.g[j] = op.gather(PDLP_COL(cols[idx]));
+      }
+    };
+
+    // finish(): multiply, reduce, epilogue, release the stage
+    auto finish = [&](int ci, Work<Op>& w) {
+      const int it = ci - cb;
+      const int s = it % Cfg::STAGES;
       const unsigned char* st = smem + (size_t)s * Cfg::STAGE_BYTES;
       const Chunk ch = *reinterpret_cast<const Chunk*>(st + Cfg::DESC_OFF);
       if (ch.meta & CHUNK_LONG) {
@@ -212,7 +294,7 @@ stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
         T acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = T(0);
-        for (int e = ch.nnz_begin + tid; e < ch.nnz_end; e += Cfg::NCONS) op.fma(acc, A.vals[e], A.colidx[e]);
+        for (int e = ch.nnz_begin + tid; e < ch.nnz_end; e += Cfg::NCONS) op.mac(acc, A.vals[e], op.gather(A.colidx[e]));
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
 #pragma unroll
@@ -229,10 +311,10 @@ stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
             double t = 0.0;
-            for (int w = 0; w < Cfg::NWARPS; ++w) t += s_red[w][v];
+            for (int ww = 0; ww < Cfg::NWARPS; ++ww) t += s_red[ww][v];
             tot[v] = (T)t;
           }
-          op.row(ch.row_begin, tot, red);
+          op.row_finish(ch.row_begin, op.row_load(ch.row_begin), tot, red);
         }
       } else {
         const int* rptr = reinterpret_cast<const int*>(st + Cfg::RPTR_OFF);
@@ -242,46 +324,100 @@ stream_kernel(const CsrView<typename Op::value_type> A, Op op) {
         const int tl = (ch.meta >> 16) & 0xf;
         const int tpr = 1 << tl;
         const int groups = 32 >> tl;
-        const int g = lane >> tl;
         const int li = lane & (tpr - 1);
+        // ---- round 0: gathers were issued by issue() ----
+        T acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = T(0);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int idx = w.i0 + j * tpr;
+          if (idx < w.e) op.mac(acc, vals[idx], w.g[j]);
+        }
+        for (int i = w.i0 + U * tpr; i < w.e; i += U * tpr) {       // rows longer than U * tpr
+          typename Op::Gather g[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int idx = i + j * tpr;
+            if (idx < w.e) g[j] = op.gather(PDLP_COL(cols[idx]));
+          }
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int idx = i + j * tpr;
+            if (idx < w.e) op.mac(acc, vals[idx], g[j]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          for (int o = tpr >> 1; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
+        }
+#ifndef PDLP_DBG_NOEPI
+        if (w.valid && li == 0) op.row_finish(w.row, w.ctx, acc, red);
+#else
+        if (w.valid && li == 0) red[0] += (double)acc[0];
+#endif
+        // ---- further rounds (chunks with more rows than one pass of the CTA covers) ----
         const int rpw = (nrows + Cfg::NWARPS - 1) / Cfg::NWARPS;
         const int rw0 = warp * rpw;
         const int rw1 = min(nrows, rw0 + rpw);
-        const int roff = ch.row_begin - (ch.row_begin & ~3);
-        const int ebase = ch.nnz_begin & ~3;
-        for (int rr = rw0; rr < rw1; rr += groups) {
-          const int r = rr + g;
-          const bool valid = r < rw1;
-          int b = 0, e = 0;
-          if (valid) {
-            b = rptr[roff + r] - ebase;
-            e = rptr[roff + r + 1] - ebase;
-          }
-          T acc[NV];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) acc[v] = T(0);
-          for (int i = b + li; i < e; i += U * tpr) {
-            int cj[U];
-            T vj[U];
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-              const int idx = i + j * tpr;
-              const bool ok = idx < e;
-              cj[j] = ok ? cols[idx] : -1;
-              vj[j] = ok ? vals[idx] : T(0);
+        if (rw0 + groups < rw1) {
+          const int roff = ch.row_begin - (ch.row_begin & ~3);
+          const int ebase = ch.nnz_begin & ~3;
+          for (int rr = rw0 + groups; rr < rw1; rr += groups) {
+            const int r = rr + (lane >> tl);
+            const bool valid = r < rw1;
+            int b = 0, e = 0;
+            typename Op::Ctx ctx;
+            if (valid) {
+              b = rptr[roff + r] - ebase;
+              e = rptr[roff + r + 1] - ebase;
+              if (li == 0) ctx = op.row_load(ch.row_begin + r);
             }
-            op.template fma_batch<U>(acc, vj, cj);
-          }
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            for (int o = tpr >> 1; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
+            for (int v = 0; v < NV; ++v) acc[v] = T(0);
+            for (int i = b + li; i < e; i += U * tpr) {
+              typename Op::Gather g[U];
+#pragma unroll
+              for (int j = 0; j < U; ++j) {
+                const int idx = i + j * tpr;
+                if (idx < e) g[j] = op.gather(PDLP_COL(cols[idx]));
+              }
+#pragma unroll
+              for (int j = 0; j < U; ++j) {
+                const int idx = i + j * tpr;
+                if (idx < e) op.mac(acc, vals[idx], g[j]);
+              }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              for (int o = tpr >> 1; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
+            }
+            if (valid && li == 0) op.row_finish(ch.row_begin + r, ctx, acc, red);
           }
-          if (valid && li == 0) op.row(ch.row_begin + r, acc, red);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
+    };
+
+#ifdef PDLP_DBG_NOWORK
+    for (int ci = cb; ci < ce; ++ci) {
+      const int it = ci - cb;
+      const int s = it % Cfg::STAGES;
+      mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
+    (void)issue; (void)finish;
+#else
+    Work<Op> cur, nxt;
+    if (cb < ce) issue(cb, cur);
+    for (int ci = cb; ci < ce; ++ci) {
+      if (ci + 1 < ce) issue(ci + 1, nxt);
+      finish(ci, cur);
+      cur = nxt;
+    }
+#endif
   }
 
   // ---------------- deterministic grid reduction + finalize ----------------
