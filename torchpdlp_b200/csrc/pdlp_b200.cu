@@ -33,77 +33,141 @@ static int fail(int code, const std::string& msg) {
 extern "C" const char* pdlp_last_error(void) { return g_err.c_str(); }
 
 // ---------------------------------------------------------------------------
-// plan: chunks + CTA ranges
+// plan: SELL-32-sigma slices, pieces, per-warp piece ranges (layout described in stream_spmv.cuh)
 // ---------------------------------------------------------------------------
-struct HostPlan {
-  std::vector<Chunk> chunks;
-  std::vector<int> cta_begin;
-  int grid = 0;
+struct HostSell {
+  std::vector<Piece> pieces;
+  std::vector<long long> slot_begin;   // first packed slot of each piece (+ total)
+  std::vector<int> src;                // packed slot -> CSR index, -1 = padding
+  std::vector<int> perm;               // row per (slice, lane), -1 = padding lane
+  std::vector<int> warp_begin;         // grid * W + 1
+  std::vector<int> long_rows;
+  size_t packed_bytes = 0;
+  int grid = 1;
 };
 
-static int ceil_pow2(int v) {
-  int p = 1;
-  while (p < v) p *= 2;
-  return p;
+static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int value_bytes, int W, int KB, int sigma,
+                                int long_row, int max_grid) {
+  HostSell P;
+  auto len = [&](int r) { return rowptr[r + 1] - rowptr[r]; };
+  std::vector<int> order;
+  order.reserve(rows);
+  for (int r = 0; r < rows; ++r) {
+    if (len(r) > long_row) P.long_rows.push_back(r);
+    else order.push_back(r);
+  }
+  // sort by length (descending, stable) inside windows of sigma rows: neighbours in a slice get equal lengths
+  for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {
+    const size_t w1 = std::min(order.size(), w0 + (size_t)sigma);
+    std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return len(a) > len(b); });
+  }
+  while (order.size() % 32) order.push_back(-1);
+  P.perm = order;
+  const int nsl = (int)(order.size() / 32);
+  std::vector<int> klen(nsl, 0);
+  for (int i = 0; i < nsl; ++i)
+    for (int r = 0; r < 32; ++r) {
+      const int row = order[(size_t)i * 32 + r];
+      if (row >= 0) klen[i] = std::max(klen[i], len(row));
+    }
+  std::vector<int> kbase;   // first step (position inside the row) covered by each piece
+  const int MAXSL = 16;     // StreamCfg::MAXSL
+  for (int i = 0; i < nsl;) {
+    if (klen[i] > KB) {
+      for (int k0 = 0; k0 < klen[i]; k0 += KB) {
+        Piece pc{0, i * 32, (uint16_t)std::min(KB, klen[i] - k0), 1,
+                 (k0 == 0 ? PIECE_FIRST : 0u) | (k0 + KB >= klen[i] ? PIECE_LAST : 0u)};
+        P.pieces.push_back(pc);
+        kbase.push_back(k0);
+      }
+      ++i;
+    } else {
+      int j = i, kmax = klen[i];
+      while (j + 1 < nsl && (j + 1 - i) < MAXSL && klen[j + 1] <= KB &&
+             std::max(kmax, klen[j + 1]) * (j + 2 - i) <= KB) {
+        kmax = std::max(kmax, klen[j + 1]);
+        ++j;
+      }
+      Piece pc{0, i * 32, (uint16_t)kmax, (uint16_t)(j - i + 1), PIECE_FIRST | PIECE_LAST};
+      P.pieces.push_back(pc);
+      kbase.push_back(0);
+      i = j + 1;
+    }
+  }
+  // block offsets and the slot -> CSR index map
+  const int np = (int)P.pieces.size();
+  P.slot_begin.resize(np + 1);
+  size_t bytes = 0;
+  long long slots = 0;
+  for (int p = 0; p < np; ++p) {
+    Piece& pc = P.pieces[p];
+    pc.data_off16 = (uint32_t)(bytes / 16);
+    P.slot_begin[p] = slots;
+    const long long steps = (long long)pc.klen * pc.nslices;
+    slots += steps * 32;
+    bytes += 16 + ((pc.flags & PIECE_FIRST) ? (size_t)pc.nslices * 128 : 0) + (size_t)steps * 32 * (4 + value_bytes);
+  }
+  P.slot_begin[np] = slots;
+  P.packed_bytes = bytes;
+  P.src.assign((size_t)slots, -1);
+  for (int p = 0; p < np; ++p) {
+    const Piece& pc = P.pieces[p];
+    int* dst = P.src.data() + P.slot_begin[p];
+    for (int sl = 0; sl < pc.nslices; ++sl)
+      for (int r = 0; r < 32; ++r) {
+        const int row = P.perm[(size_t)pc.perm_off + sl * 32 + r];
+        if (row < 0) continue;
+        const int L = len(row), base = rowptr[row];
+        for (int k = 0; k < pc.klen; ++k) {
+          const int kk = kbase[p] + k;
+          if (kk < L) dst[((size_t)sl * pc.klen + k) * 32 + r] = base + kk;
+        }
+      }
+  }
+  // warps: contiguous piece ranges balanced by bytes (+ a fixed per-piece cost), cut only where rows start
+  std::vector<double> pre(np + 1, 0.0);
+  for (int p = 0; p < np; ++p)
+    pre[p + 1] = pre[p] + (double)P.pieces[p].klen * P.pieces[p].nslices * 32 * (4 + value_bytes) + 256.0 +
+                 ((P.pieces[p].flags & PIECE_LAST) ? 32.0 * 40.0 * P.pieces[p].nslices : 0.0);
+  int starts = 0;
+  for (int p = 0; p < np; ++p) starts += (P.pieces[p].flags & PIECE_FIRST) ? 1 : 0;
+  P.grid = std::max(1, std::min(max_grid, (starts + W - 1) / W));
+  if (!P.long_rows.empty()) P.grid = std::max(P.grid, std::min(max_grid, (int)P.long_rows.size()));
+  const int nw = P.grid * W;
+  P.warp_begin.assign(nw + 1, np);
+  P.warp_begin[0] = 0;
+  for (int w = 1; w < nw; ++w) {
+    const double target = pre[np] * w / nw;
+    int lo = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+    lo = std::min(std::max(lo, P.warp_begin[w - 1]), np);
+    while (lo < np && !(P.pieces[lo].flags & PIECE_FIRST)) ++lo;
+    P.warp_begin[w] = lo;
+  }
+  P.warp_begin[nw] = np;
+  return P;
 }
 
-// Greedy row packing.  A chunk is a run of rows whose nonzeros fit one shared-memory stage.  The CTA's NCONS
-// consumer lanes cover it in ONE pass: threads-per-row tpr (a power of two) is sized so that a row of average
-// length needs a single batch of U gathers per lane, and the chunk takes NCONS / tpr rows.  A row longer than a
-// stage becomes a "long" chunk streamed from global memory by the whole CTA.
-static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz, int max_rows, int ncons, int U,
-                           int max_grid, double row_cost_nnz) {
-  HostPlan P;
-  int r = 0;
-  while (r < rows) {
-    const int len0 = rowptr[r + 1] - rowptr[r];
-    if (len0 > max_nnz) {
-      Chunk c{r, rowptr[r], rowptr[r + 1], CHUNK_LONG | 1u};
-      P.chunks.push_back(c);
-      ++r;
-      continue;
+// fill the piece blocks: header, row ids, and packed[slot] <- CSR[src[slot]] (cols and vals); one CTA per piece
+template <typename T>
+__global__ void pack_kernel(const Piece* pieces, const long long* slot_begin, const int* src, const int* perm,
+                            int npieces, const int* colidx, const T* vals, unsigned char* packed) {
+  for (int p = blockIdx.x; p < npieces; p += gridDim.x) {
+    const Piece pc = pieces[p];
+    unsigned char* blk = packed + (size_t)pc.data_off16 * 16u;
+    const int nslots = (int)pc.klen * pc.nslices * 32;
+    const int nrows = (pc.flags & PIECE_FIRST) ? (int)pc.nslices * 32 : 0;
+    if (threadIdx.x == 0) *reinterpret_cast<Piece*>(blk) = pc;
+    int* rdst = reinterpret_cast<int*>(blk + 16);
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) rdst[i] = perm[pc.perm_off + i];
+    int* cdst = rdst + nrows;
+    T* vdst = reinterpret_cast<T*>(cdst + nslots);
+    const int* sp = src + slot_begin[p];
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+      const int s = sp[i];
+      cdst[i] = s >= 0 ? colidx[s] : 0;
+      vdst[i] = s >= 0 ? vals[s] : T(0);
     }
-    // look ahead over up to ncons rows to estimate the local row length
-    const int look = std::min(rows, r + ncons);
-    int la = r, lnnz = 0;
-    while (la < look && (rowptr[la + 1] - rowptr[la]) <= max_nnz) { lnnz += rowptr[la + 1] - rowptr[la]; ++la; }
-    const double avg = la > r ? (double)lnnz / (la - r) : 1.0;
-    int tpr = std::min(32, ceil_pow2(std::max(1, (int)((avg * 1.15 + U - 1) / U))));
-    int want_rows = std::max(1, ncons / tpr);
-    int e = r, nnz = 0;
-    while (e < rows && (e - r) < max_rows && (e - r) < want_rows) {
-      const int len = rowptr[e + 1] - rowptr[e];
-      if (len > max_nnz || nnz + len > max_nnz) break;
-      nnz += len;
-      ++e;
-    }
-    const int nr = e - r;     // >= 1: the first row fits
-    int tl = 0;
-    while ((1 << tl) < tpr) ++tl;
-    Chunk c{r, rowptr[r], rowptr[e], (uint32_t)nr | ((uint32_t)tl << 16)};
-    P.chunks.push_back(c);
-    r = e;
   }
-  // contiguous ranges balanced by weight = nnz + row_cost_nnz * rows + fixed per-chunk cost
-  const int nc = (int)P.chunks.size();
-  std::vector<double> pre(nc + 1, 0.0);
-  for (int i = 0; i < nc; ++i) {
-    const Chunk& c = P.chunks[i];
-    const int nr = (c.meta & CHUNK_LONG) ? 1 : (int)(c.meta & 0xffff);
-    pre[i + 1] = pre[i] + (double)(c.nnz_end - c.nnz_begin) + row_cost_nnz * nr + 64.0;
-  }
-  P.grid = std::max(1, std::min(max_grid, nc));
-  P.cta_begin.resize(P.grid + 1);
-  P.cta_begin[0] = 0;
-  for (int p = 1; p < P.grid; ++p) {
-    const double target = pre[nc] * p / P.grid;
-    int lo = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
-    lo = std::max(lo, P.cta_begin[p - 1]);
-    lo = std::min(lo, nc);
-    P.cta_begin[p] = lo;
-  }
-  P.cta_begin[P.grid] = nc;
-  return P;
 }
 
 // ---------------------------------------------------------------------------
@@ -111,16 +175,24 @@ static HostPlan build_plan(const std::vector<int>& rowptr, int rows, int max_nnz
 // ---------------------------------------------------------------------------
 template <typename T>
 struct DeviceCsr {
+  // CSR master copy (setup-time kernels, long rows)
   int* rowptr = nullptr;
   int* colidx = nullptr;
   T* vals = nullptr;
-  Chunk* chunks = nullptr;
-  int* cta_begin = nullptr;
+  // SELL-32-sigma packed copy (hot kernels)
+  unsigned char* packed = nullptr;
+  Piece* pieces = nullptr;
+  long long* slot_begin = nullptr;
+  int* src = nullptr;
+  int* perm = nullptr;
+  int* warp_begin = nullptr;
+  int* long_rows = nullptr;
   double* partials = nullptr;
   unsigned int* ticket = nullptr;
-  int rows = 0, cols = 0, nnz = 0, grid = 0, nchunks = 0, nlong = 0;
-  CsrView<T> view() const {
-    return CsrView<T>{rowptr, colidx, vals, chunks, cta_begin, partials, ticket, rows};
+  int rows = 0, cols = 0, nnz = 0, grid = 0, npieces = 0, nlong = 0;
+  size_t packed_bytes = 0;
+  SellView<T> view() const {
+    return SellView<T>{packed, pieces, warp_begin, long_rows, nlong, rowptr, colidx, vals, partials, ticket};
   }
 };
 
@@ -129,7 +201,7 @@ struct pdlp_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   int64_t m = 0, n = 0, m_ineq = 0, nnz = 0;
-  int sms = 0, ctas_per_sm = 2;
+  int sms = 0, ctas_per_sm = 1;
   bool scaled = false;
   bool have_prev = false;
   bool infeas = false;    // host mirror of Scalars::infeas_detect
@@ -183,20 +255,27 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
   return cudaGetLastError();
 }
 
+// (re)fill the packed copy from the CSR master copy (after create and after every scaling pass)
+template <typename T>
+static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
+  pdlp_engine* B = E->base;
+  if (A.npieces == 0) return 0;
+  pack_kernel<T><<<std::min(A.npieces, B->sms * 16), 256, 0, B->stream>>>(A.pieces, A.slot_begin, A.src, A.perm,
+                                                                         A.npieces, A.colidx, A.vals, A.packed);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nnz, const int32_t* rowptr,
-                      const int32_t* colidx, const void* vals, double row_cost_nnz) {
+                      const int32_t* colidx, const void* vals) {
   cudaStream_t st = E->base->stream;
   A.rows = rows;
   A.cols = cols;
   A.nnz = nnz;
-  const size_t pad = 16;
-  ALLOC(A.rowptr, rows + 1 + pad);
-  ALLOC(A.colidx, nnz + pad);
-  ALLOC(A.vals, nnz + pad);
-  CU(cudaMemsetAsync(A.rowptr, 0, sizeof(int) * (rows + 1 + pad), st));
-  CU(cudaMemsetAsync(A.colidx, 0, sizeof(int) * (nnz + pad), st));
-  CU(cudaMemsetAsync(A.vals, 0, sizeof(T) * (nnz + pad), st));
+  ALLOC(A.rowptr, rows + 1);
+  ALLOC(A.colidx, nnz);
+  ALLOC(A.vals, nnz);
   CU(cudaMemcpyAsync(A.rowptr, rowptr, sizeof(int) * (rows + 1), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(A.colidx, colidx, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(A.vals, vals, sizeof(T) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
@@ -207,19 +286,32 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   for (int r = 0; r < rows; ++r)
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   using Cfg = StreamCfg<T>;
-  HostPlan P = build_plan(h_rowptr, rows, Cfg::MAX_CHUNK_NNZ, Cfg::MAX_CHUNK_ROWS, Cfg::NCONS, Cfg::U,
-                          E->base->sms * E->base->ctas_per_sm, row_cost_nnz);
+  HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW,
+                               E->base->sms * E->base->ctas_per_sm);
+  if (P.packed_bytes / 16 >= 0xffffffffull) return fail(PDLP_ERR_INVALID, "packed matrix exceeds 64 GiB");
   A.grid = P.grid;
-  A.nchunks = (int)P.chunks.size();
-  A.nlong = 0;
-  for (const Chunk& c : P.chunks) A.nlong += (c.meta & CHUNK_LONG) ? 1 : 0;
-  ALLOC(A.chunks, P.chunks.size() + 1);
-  ALLOC(A.cta_begin, P.cta_begin.size());
+  A.npieces = (int)P.pieces.size();
+  A.nlong = (int)P.long_rows.size();
+  A.packed_bytes = P.packed_bytes;
+  ALLOC(A.packed, P.packed_bytes + 16);
+  ALLOC(A.pieces, P.pieces.size() + 1);
+  ALLOC(A.slot_begin, P.slot_begin.size());
+  ALLOC(A.src, P.src.size() + 1);
+  ALLOC(A.perm, P.perm.size() + 32);
+  ALLOC(A.warp_begin, P.warp_begin.size());
+  ALLOC(A.long_rows, P.long_rows.size() + 1);
   ALLOC(A.partials, (size_t)P.grid * MAX_RED);
   ALLOC(A.ticket, 1);
-  CU(cudaMemcpyAsync(A.chunks, P.chunks.data(), sizeof(Chunk) * P.chunks.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A.cta_begin, P.cta_begin.data(), sizeof(int) * P.cta_begin.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.pieces, P.pieces.data(), sizeof(Piece) * P.pieces.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.slot_begin, P.slot_begin.data(), sizeof(long long) * P.slot_begin.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.src, P.src.data(), sizeof(int) * P.src.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.perm, P.perm.data(), sizeof(int) * P.perm.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.warp_begin, P.warp_begin.data(), sizeof(int) * P.warp_begin.size(), cudaMemcpyHostToDevice, st));
+  if (!P.long_rows.empty())
+    CU(cudaMemcpyAsync(A.long_rows, P.long_rows.data(), sizeof(int) * P.long_rows.size(), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(A.ticket, 0, sizeof(unsigned int), st));
+  int rc = repack<T>(E, A);
+  if (rc) return rc;
   CU(cudaStreamSynchronize(st));
   return 0;
 }
@@ -239,7 +331,6 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   const int m = (int)B->m, n = (int)B->n, nnz = (int)B->nnz;
   cudaStream_t st = B->stream;
   // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
-  const double per_nnz = sizeof(T) + 4.0;
   {
     using Rep = DualOp<T, false, false>;
     CU(cudaFuncSetAttribute(stream_kernel<Rep>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::SMEM_BYTES));
@@ -247,9 +338,9 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel<Rep>, StreamCfg<T>::NT, StreamCfg<T>::SMEM_BYTES));
     B->ctas_per_sm = std::max(1, occ);
   }
-  int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals, 5.0 * sizeof(T) / per_nnz);
+  int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals);
   if (rc) return rc;
-  rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals, 8.0 * sizeof(T) / per_nnz);
+  rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals);
   if (rc) return rc;
   ALLOC(E->c, n); ALLOC(E->l, n); ALLOC(E->u, n); ALLOC(E->q, m);
   ALLOC(E->xp, n); ALLOC(E->xsum, n); ALLOC(E->xlast, n); ALLOC(E->X4, n);
@@ -560,6 +651,9 @@ static int engine_ruiz(EngineT<T>* E, int max_iter, double eps, int* rounds_out)
   cudaFree(dcs);
   B->scaled = true;
   if (rounds_out) *rounds_out = rounds;
+  rc = repack<T>(E, E->K);
+  if (!rc) rc = repack<T>(E, E->Kt);
+  if (rc) return rc;
   return refresh_norms<T>(E);
 }
 
@@ -594,6 +688,9 @@ static int engine_pock_chambolle(EngineT<T>* E) {
   cudaFree(drs);
   cudaFree(dcs);
   B->scaled = true;
+  rc = repack<T>(E, E->K);
+  if (!rc) rc = repack<T>(E, E->Kt);
+  if (rc) return rc;
   return refresh_norms<T>(E);
 }
 
