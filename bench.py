@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- PDHG iterations/sec of the B200 engine on BASELINE.json's config 2
+(synthetic bounded LP, m=100k, n=200k, 5M nnz, fp64, restarts + adaptive steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one restart block of the hot path: 40 PDHG iterations (2 fused kernels
+each) followed by the restart test (averages, 3 KKT errors in one pass over K and
+one over K^T, criteria, restart).  `value` = iterations/sec with the LP resident in
+HBM (CUDA events, max over ranks); `e2e` = iterations/sec of whole solves through
+the public API `pdlp_algorithm` starting from HOST tensors (pinned), i.e. including
+the H2D copy of the LP, the engine build, the power iteration, every restart test and
+the D2H copy of the solution.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "pdhg_iterations_per_sec"
+UNIT = "it/s"
+WORKLOAD = "cfg2: synthetic bounded LP m=100000 n=200000 nnz=5000000 (50/row), fp64, restarts + adaptive step + primal weight"
+RESTART_PERIOD = 40
+KERNELS_PER_STEP = 2 * RESTART_PERIOD + 6      # 80 iteration kernels + flush, 2 KKT, decide, apply, post
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_lp():
+    from torchpdlp_b200 import synthetic
+    return synthetic.uniform_rows_lp()
+
+
+# ----------------------------------------------------------------------------- CPU arms
+class OracleStepper:
+    """Adaptive PDHG iterations of the oracle port (torch CPU) on the cfg2 LP, state kept between calls."""
+
+    def __init__(self, lp, layout):
+        from oracle import pdlp_oracle as orc
+        torch.set_default_dtype(torch.float64)
+        self.orc = orc
+        c, K, q, self.m_ineq, l, u = lp.torch_tensors(layout=layout)
+        self.op = orc.Operator(K)
+        self.c, self.q, self.l, self.u = (v.reshape(-1) for v in (c, q, l, u))
+        self.x, self.y = torch.zeros(lp.n), torch.zeros(lp.m)
+        self.eta = 0.9 / 18.2
+        self.omega = float(torch.linalg.norm(self.c) / torch.linalg.norm(self.q))
+        self.k = 0
+
+    def run(self, iters):
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            self.k += 1
+            self.x, self.y, w, self.eta = self.orc.adaptive_one_step_pdhg(
+                self.x, self.y, self.c, self.q, self.op, self.l, self.u, self.m_ineq, self.eta, self.omega, 1.0, self.k)
+        return time.perf_counter() - t0
+
+
+def oracle_rate(lp, layout, iters, warm=1):
+    st = OracleStepper(lp, layout)
+    st.run(warm)
+    return iters / st.run(iters)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for this workload.  torchPDLP is pure
+    Python/torch and /root/reference does not travel to the GPU box, so this times the oracle
+    port (oracle/pdlp_oracle.py, validated bit-for-bit against the executed reference on config
+    1) with K as a torch sparse COO tensor -- the only sparse layout the reference itself can
+    run -- on all host threads.  Each step = a bounded sample of
+    adaptive PDHG iterations, sized so the whole run stays within a few minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lp = make_lp()
+    st = OracleStepper(lp, "coo")
+    t_iter = st.run(1)
+    t_iter = min(t_iter, st.run(1))
+    per_step = int(max(1, min(8, 100.0 / (max(args.steps, 1) * t_iter))))
+    for _ in range(min(args.warmup, 2)):
+        st.run(1)
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += st.run(per_step)
+    value = args.steps * per_step / dt
+    csr = oracle_rate(lp, "csr", 20)
+    cores = torch.get_num_threads()
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": f"{per_step} adaptive PDHG iterations (bounded sample)",
+                   "layout": "torch sparse COO (reference layout)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x {per_step} adaptive iterations of the oracle port, torch sparse COO, "
+                                   f"{cores} threads of {os.cpu_count()} cpus; same port on torch sparse CSR (MKL): {csr:.1f} it/s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_engine(args):
+    import torch.distributed as dist
+    from torchpdlp_b200.engine import Engine
+    from torchpdlp_b200.primal_dual_hybrid_gradient import initial_step, pdlp_algorithm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_default_dtype(torch.float64)
+    lp = make_lp()
+    eng = Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u, device=dev)
+    torch.manual_seed(0)
+    eta, omega, sigma = initial_step(eng, 100)
+
+    def reset():
+        eng.set_iterate(None, None)
+        eng.set_counters(0, 0)
+        eng.set_step(eta, omega, 1.0, adaptive=True)
+        eng.set_options(1e-4, True, False, 1e-4)
+
+    def step():
+        eng.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
+        return eng.restart_check(False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    reset()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # per-kernel durations, CUDA events on the engine's stream (cannot be placed inside the graph replay)
+    prim_ms, dual_ms = eng.time_kernels(200)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    iters = RESTART_PERIOD * args.steps
+    value = world * iters / (ms * 1e-3)          # every rank solves its own LP (replicas): whole-job aggregate
+
+    # ---- e2e: whole solves through the public API from pinned host tensors ----
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr")
+    host = [t.pin_memory() for t in (K.crow_indices(), K.col_indices(), K.values(), c, q, l, u)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    Kh = torch.sparse_csr_tensor(host[0], host[1], host[2], size=K.shape)
+    n_solves = max(1, min(3, args.steps))
+    from torchpdlp_b200 import _cache
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(n_solves):
+        _cache.clear()
+        torch.manual_seed(0)
+        x, obj, k, n, j, status, secs = pdlp_algorithm(Kh, m_ineq, host[3], host[4], host[5], host[6], dev, verbose=False,
+                                                       adaptive=True, primal_update=True)
+        x_host = x.cpu()
+        e2e_iters += k
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_iters / e2e_s
+    d2h = x_host.numel() * x_host.element_size() + 64
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        b_iter = eng.bytes_per_iteration
+        dual_bytes = 12 * lp.nnz + 4 * (lp.m + 1) + 8 * lp.n + 40 * lp.m       # K stream + gather xbar + 5 m-side streams
+        ach = dual_bytes / (dual_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        # bounded CPU sample of the same workload (oracle port, all host threads)
+        cores = torch.get_num_threads()
+        cpu_coo = oracle_rate(lp, "coo", 8)
+        cpu_csr = oracle_rate(lp, "csr", 40)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "40 PDHG iterations + restart test (3 KKT errors)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no data-path collective)",
+                       "l2": "working set 140 MB of matrix+vectors per iteration > 126 MB L2; no explicit flush",
+                       "sigma_max": sigma, "bytes_per_iteration": b_iter},
+            "us_per_iteration": 1e3 * ms / iters,
+            "iteration_roofline_frac": b_iter / (ms * 1e-3 / iters) / 1e9 / peak,
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": f"{n_solves} whole solves (pdlp_algorithm from pinned host tensors to tolerance 1e-4: "
+                            f"{e2e_iters // n_solves} iterations each, status {status}), {e2e_s / n_solves:.3f} s per solve"},
+            "roofline": {"bound": "hbm", "kernel": "stream_kernel<DualOp> (K xbar + dual update + step rule)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": dual_bytes,
+                         "launch_ms": dual_ms, "primal_launch_ms": prim_ms},
+            "cpu_baseline": {"value": cpu_coo, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"8 adaptive PDHG iterations of the oracle port on the same LP, torch sparse COO "
+                                       f"(the reference's sparse layout), {cores} threads; torch sparse CSR (MKL): {cpu_csr:.1f} it/s"},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,12 @@ int pdlp_set_counters(pdlp_handle h, int64_t k, int32_t t);
  * test (:77-78,:126).  use_graph != 0 replays a cached CUDA graph.  Async.    */
 int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int use_graph);
 
+/* Measurement aid for bench.py: run n_iters iterations WITHOUT a graph, bracketing every
+ * launch of the two iteration kernels with CUDA events on the engine's stream, and return
+ * the average device time per launch (milliseconds) of the primal (K^T y) and dual (K xbar)
+ * kernels.  Advances the solver state like pdlp_iterate.  Synchronises. */
+int pdlp_time_kernels(pdlp_handle h, int n_iters, float* host_primal_ms, float* host_dual_ms);
+
 /* Restart test + restart epilogue (:115-177): averages, the three KKT errors
  * with ONE pass over K and one over K^T, the sufficient / necessary / artificial
  * criteria, candidate selection, primal-weight update, KKT_first, termination

@@ -487,6 +487,35 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
 }
 
 template <typename T>
+static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, float* dual_ms) {
+  cudaStream_t st = E->base->stream;
+  std::vector<cudaEvent_t> ev(3 * (size_t)n_iters);
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  for (int i = 0; i < n_iters; ++i) {
+    PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
+    DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    CU(cudaEventRecord(ev[3 * i], st));
+    CU(launch_stream(E->Kt, p, st));
+    CU(cudaEventRecord(ev[3 * i + 1], st));
+    CU(launch_stream(E->K, d, st));
+    CU(cudaEventRecord(ev[3 * i + 2], st));
+  }
+  CU(cudaStreamSynchronize(st));
+  double tp = 0.0, td = 0.0;
+  for (int i = 0; i < n_iters; ++i) {
+    float a = 0.f, b = 0.f;
+    CU(cudaEventElapsedTime(&a, ev[3 * i], ev[3 * i + 1]));
+    CU(cudaEventElapsedTime(&b, ev[3 * i + 1], ev[3 * i + 2]));
+    tp += a;
+    td += b;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *primal_ms = (float)(tp / n_iters);
+  *dual_ms = (float)(td / n_iters);
+  return 0;
+}
+
+template <typename T>
 static int enqueue_kkt(EngineT<T>* E, cudaStream_t st) {
   pdlp_engine* B = E->base;
   KktColsOp<T> a{E->Y4, E->X4, E->c, E->l, E->u, B->scaled ? E->dcol : nullptr, E->S};
@@ -975,6 +1004,12 @@ extern "C" int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int u
   CHECK_HANDLE(h);
   if (n_iters < 0) return fail(PDLP_ERR_INVALID, "n_iters < 0");
   return DISPATCH(h, engine_iterate, n_iters, save_previous, use_graph);
+}
+
+extern "C" int pdlp_time_kernels(pdlp_handle h, int n_iters, float* host_primal_ms, float* host_dual_ms) {
+  CHECK_HANDLE(h);
+  if (n_iters <= 0 || !host_primal_ms || !host_dual_ms) return fail(PDLP_ERR_INVALID, "bad argument");
+  return DISPATCH(h, engine_time_kernels, n_iters, host_primal_ms, host_dual_ms);
 }
 
 extern "C" int pdlp_restart_check(pdlp_handle h, int force, pdlp_check* host_out) {

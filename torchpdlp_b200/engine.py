@@ -180,6 +180,12 @@ class Engine:
     def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = True):
         check(self.lib.pdlp_iterate(self.h, int(n_iters), int(bool(save_previous)), int(bool(use_graph))))
 
+    def time_kernels(self, n_iters: int):
+        """Average device milliseconds per launch of the (primal, dual) iteration kernels."""
+        a, b = C.c_float(), C.c_float()
+        check(self.lib.pdlp_time_kernels(self.h, int(n_iters), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def restart_check(self, force: bool = False) -> Check:
         chk = Check()
         check(self.lib.pdlp_restart_check(self.h, int(bool(force)), C.byref(chk)))
