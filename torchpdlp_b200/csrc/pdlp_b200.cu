@@ -251,8 +251,17 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  stream_kernel<Op><<<A.grid, StreamCfg<T>::NT, StreamCfg<T>::SMEM_BYTES, st>>>(A.view(), op);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(A.grid);
+  cfg.blockDim = dim3(StreamCfg<T>::NT);
+  cfg.dynamicSmemBytes = StreamCfg<T>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, stream_kernel<Op>, A.view(), op);
 }
 
 // (re)fill the packed copy from the CSR master copy (after create and after every scaling pass)

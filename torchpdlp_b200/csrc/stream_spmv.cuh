@@ -162,8 +162,6 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   __shared__ double s_red[Cfg::W][NR > NV ? NR : NV];
   __shared__ int s_last;
 
-  if (!op.begin()) return;
-
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -196,6 +194,16 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
       mbar_arrive_expect_tx(&full_bar[warp][s], bytes);
       tma_load_1d(ring + (size_t)s * Cfg::STAGE_BYTES, A.packed + (size_t)d.data_off16 * 16u, bytes, &full_bar[warp][s]);
     }
+  }
+
+  // Programmatic dependent launch: everything above touched only the (constant) matrix plan, so it overlaps the
+  // tail of the previous kernel in the stream / graph.  From here on we read what that kernel wrote.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!op.begin()) {
+    // drain the copies already in flight before the CTA may retire
+    for (int s = 0; s < Cfg::S && pb + s < pe; ++s) mbar_wait(&full_bar[warp][s], 0);
+    return;
   }
 
   // ---------------- long rows: one row per CTA, straight from CSR ----------------
