@@ -190,6 +190,35 @@ int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u);
 /* Current (possibly scaled) values of K in the caller's CSR order (nnz values). */
 int pdlp_get_matrix_values(pdlp_handle h, void* K_vals);
 
+/* ---- row-partitioned engine (multi-GPU) ------------------
+ * Each rank builds an ordinary handle on ITS rows of K (m = local rows, m_ineq = local
+ * ">=" rows; n, c, l, u replicated) and marks it sharded.  K^T y = sum over ranks of the
+ * local partial, so the column side of every pass is split around a host-side allreduce
+ * (NCCL through torch.distributed, on the handle's stream):
+ *
+ *   iteration     pdlp_shard_kty(buf)        buf[0..n) = K_g^T y_g, buf[n..n+4) = partial norms
+ *                 allreduce(buf, n + 4)
+ *                 pdlp_shard_step(buf, save) step rule of the PREVIOUS iteration (global norms),
+ *                                            primal update, local dual kernel
+ *   restart test  pdlp_shard_rule_pack / allreduce(4) / pdlp_shard_rule_apply   (pending rule)
+ *                 pdlp_shard_check_begin(buf3)   buf3[3j+v] = K_g^T Y_g for the 3 iterates
+ *                 allreduce(buf3, 3n)
+ *                 pdlp_shard_check_mid(buf3, buf9)   column sums (replicated), row sums (partial)
+ *                 allreduce(buf9, 9)
+ *                 pdlp_shard_check_decide(buf9, force, buf1)   criteria + restart, ||dy_restart||^2 partial
+ *                 allreduce(buf1, 1)
+ *                 pdlp_shard_check_end(buf1, out)
+ * All buffers are device pointers to doubles owned by the caller.                     */
+int pdlp_shard_enable(pdlp_handle h, double q_norm_global, double c_norm);
+int pdlp_shard_kty(pdlp_handle h, double* buf);
+int pdlp_shard_step(pdlp_handle h, const double* buf, int save_previous);
+int pdlp_shard_rule_pack(pdlp_handle h, double* buf4);
+int pdlp_shard_rule_apply(pdlp_handle h, const double* buf4);
+int pdlp_shard_check_begin(pdlp_handle h, double* buf3);
+int pdlp_shard_check_mid(pdlp_handle h, const double* buf3, double* buf9);
+int pdlp_shard_check_decide(pdlp_handle h, const double* buf9, int force, double* buf1);
+int pdlp_shard_check_end(pdlp_handle h, const double* buf1, pdlp_check* host_out);
+
 /* ---- whole solve --------------------------------------------------------------
  * pdlp_algorithm (primal_dual_hybrid_gradient.py:7-181) driven from C++:
  * restart loop, counters k / n / j with the reference's accounting, KKT-pass and

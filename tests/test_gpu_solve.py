@@ -111,3 +111,20 @@ def test_cfg2_full_size_against_oracle(idx):
     assert np.linalg.norm(viol) <= 1e-4 * (1 + np.linalg.norm(lp.q)) * (1 + 1e-9)
     assert np.all(xv >= lp.l - 1e-12) and np.all(xv <= lp.u + 1e-12)
     assert rel(float(lp.c @ xv), obj) < 1e-12
+
+
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_sharded_entry_points_single_rank(adaptive, pw, cfg1):
+    """The pdlp_shard_* kernels (partial SpMV -> [allreduce] -> element-wise epilogues, deferred step
+    rule) with world size 1 reproduce the fused single-GPU engine and the executed reference."""
+    from torchpdlp_b200.sharded import build_rank_engine
+    torch.set_default_dtype(torch.float64)
+    gold = [r for r in CFG1_RUNS if r["options"] == dict(ruiz=False, fishnet=False, adaptive=adaptive, primal_weight=pw)][0]["reference"]
+    solver = build_rank_engine(cfg1.K, cfg1.m_ineq, cfg1.c, cfg1.q, cfg1.l, cfg1.u)
+    torch.manual_seed(0)
+    x, y, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=pw)
+    assert status == gold["status"] and n == gold["n"]
+    if adaptive:
+        assert abs(k - gold["k"]) <= 40 and rel(obj, gold["obj"]) < 2e-6
+    else:
+        assert (k, j) == (gold["k"], gold["j"]) and rel(obj, gold["obj"]) < 1e-9

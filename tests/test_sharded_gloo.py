@@ -1,0 +1,97 @@
+"""CPU: the row-partitioned orchestration under torch.distributed/gloo with world_size 2.
+
+The per-rank device work is a torch-CPU test double of the pdlp_shard_* calls
+(tests/fake_shard_prims.py); what is tested here is torchpdlp_b200.sharded: the row partition,
+the collectives, the deferred step rule and the restart protocol, against the oracle's
+single-process solve of the same LP."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, adaptive, primal_update, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_default_dtype(torch.float64)
+    from fake_shard_prims import FakeShardPrims
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.sharded import ShardedSolver, partition_rows
+    lp = synthetic.feasible_lp()
+    cuts = partition_rows(lp.K.indptr, world)
+    r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+    mi_local = min(max(lp.m_ineq - r0, 0), r1 - r0)
+    prims = FakeShardPrims(lp.K[r0:r1], mi_local, lp.c, lp.q[r0:r1], lp.l, lp.u)
+    solver = ShardedSolver(prims)
+    torch.manual_seed(0)
+    x, y_local, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=primal_update)
+    ys = [torch.zeros(int(cuts[i + 1] - cuts[i])) for i in range(world)] if rank == 0 else None
+    dist.gather(y_local, ys, dst=0)
+    if rank == 0:
+        out.put(dict(obj=obj, k=k, n=n, j=j, status=status, sigma=sigma, x=x.numpy(), y=torch.cat(ys).numpy(),
+                     collectives=solver.collectives, cuts=cuts.tolist()))
+    dist.destroy_process_group()
+
+
+def run_world(world, adaptive, primal_update):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, adaptive, primal_update, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=600)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("adaptive,primal_update", [(False, False), (True, True)])
+def test_two_rank_solve_matches_oracle(adaptive, primal_update):
+    from oracle import pdlp_oracle as orc
+    from torchpdlp_b200 import synthetic
+    torch.set_default_dtype(torch.float64)
+    res = run_world(2, adaptive, primal_update)
+    lp = synthetic.feasible_lp()
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr")
+    torch.manual_seed(0)
+    sol = orc.pdlp_algorithm(K, m_ineq, c, q, l, u, adaptive=adaptive, primal_update=primal_update, backend="scipy")
+    assert res["status"] == sol.status == "Solved"
+    assert res["n"] == sol.n
+    if adaptive:
+        assert abs(res["k"] - sol.k) <= 40 and abs(res["obj"] - sol.prim_obj) <= 2e-6 * abs(sol.prim_obj)
+    else:
+        assert (res["k"], res["j"]) == (sol.k, sol.j)
+        assert abs(res["obj"] - sol.prim_obj) <= 1e-9 * abs(sol.prim_obj)
+        np.testing.assert_allclose(res["x"], sol.x.numpy(), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(res["y"], sol.y.numpy(), rtol=0, atol=1e-9)
+    assert abs(res["sigma"] - sol.sigma_max) <= 1e-9 * sol.sigma_max
+    # one exchange per iteration + 4 per restart test + setup (norm, 2 per power-iteration round + 1)
+    assert res["collectives"] == res["k"] + 4 * (res["k"] // 40) + 1 + 100 + 1
+
+
+def test_partition_rows_balances_nnz():
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.sharded import partition_rows
+    lp = synthetic.powerlaw_rows_lp(1600, 400, 4000, max_nnz=500, seed=1)
+    for parts in (2, 4, 8):
+        cuts = partition_rows(lp.K.indptr, parts)
+        assert cuts[0] == 0 and cuts[-1] == lp.m and np.all(np.diff(cuts) > 0)
+        nnz = np.diff(lp.K.indptr[cuts])
+        assert nnz.max() <= 1.35 * nnz.mean()

@@ -79,6 +79,15 @@ SYMBOLS = {
     "pdlp_set_scaling": (_I, [_P, _P, _P]),
     "pdlp_get_problem": (_I, [_P, _P, _P, _P, _P]),
     "pdlp_get_matrix_values": (_I, [_P, _P]),
+    "pdlp_shard_enable": (_I, [_P, _D, _D]),
+    "pdlp_shard_kty": (_I, [_P, _P]),
+    "pdlp_shard_step": (_I, [_P, _P, _I]),
+    "pdlp_shard_rule_pack": (_I, [_P, _P]),
+    "pdlp_shard_rule_apply": (_I, [_P, _P]),
+    "pdlp_shard_check_begin": (_I, [_P, _P]),
+    "pdlp_shard_check_mid": (_I, [_P, _P, _P]),
+    "pdlp_shard_check_decide": (_I, [_P, _P, _I, _P]),
+    "pdlp_shard_check_end": (_I, [_P, _P, C.POINTER(Check)]),
     "pdlp_solve": (_I, [_P, C.POINTER(SolveOptions), C.POINTER(SolveResult), C.POINTER(Check)]),
 }
 

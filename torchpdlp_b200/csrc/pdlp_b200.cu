@@ -221,6 +221,7 @@ struct EngineT {
   T *kty_old = nullptr, *lam_prev = nullptr;   // infeasibility detection state
   Scalars* S = nullptr;
   double* ew_partials = nullptr;
+  double* kkt_partials = nullptr;   // sharded KKT column sums: ew_grid x 16
   unsigned int* ew_ticket = nullptr;
   int ew_grid = 0;
   // cached graphs for pdlp_iterate
@@ -362,6 +363,7 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   ALLOC(E->S, 1);
   E->ew_grid = B->sms * 4;
   ALLOC(E->ew_partials, 2 * E->ew_grid);
+  ALLOC(E->kkt_partials, 16 * E->ew_grid);
   ALLOC(E->ew_ticket, 1);
   CU(cudaMemsetAsync(E->ew_ticket, 0, sizeof(unsigned int), st));
   CU(cudaMemcpyAsync(E->c, c, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
@@ -538,6 +540,19 @@ static void fill_residuals(pdlp_residuals* o, const Resid& r) {
   o->pr = r.pr; o->dr = r.dr; o->gap = r.gap; o->prim_obj = r.prim_obj; o->adj_dual = r.adj_dual; o->kkt = r.kkt;
   o->pr_unscaled = r.pr_u; o->dr_unscaled = r.dr_u;
 }
+static void fill_check(pdlp_check* out, const Scalars& h) {
+  out->kind = h.chk_kind;
+  out->use_average = h.chk_use_avg;
+  out->t = h.chk_t;
+  out->solved = h.chk_solved;
+  out->k = h.chk_k;
+  out->omega = h.omega;
+  out->kkt_current = h.kkt_cur;
+  out->kkt_average = h.kkt_avg;
+  out->kkt_previous = h.kkt_prev;
+  out->kkt_first_new = h.kkt_first;
+  fill_residuals(&out->point, h.point);
+}
 
 template <typename T>
 static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
@@ -559,19 +574,7 @@ static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
   Scalars h;
   CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (out) {
-    out->kind = h.chk_kind;
-    out->use_average = h.chk_use_avg;
-    out->t = h.chk_t;
-    out->solved = h.chk_solved;
-    out->k = h.chk_k;
-    out->omega = h.omega;
-    out->kkt_current = h.kkt_cur;
-    out->kkt_average = h.kkt_avg;
-    out->kkt_previous = h.kkt_prev;
-    out->kkt_first_new = h.kkt_first;
-    fill_residuals(&out->point, h.point);
-  }
+  if (out) fill_check(out, h);
   return 0;
 }
 
@@ -730,6 +733,97 @@ static int engine_pock_chambolle(EngineT<T>* E) {
   if (!rc) rc = repack<T>(E, E->Kt);
   if (rc) return rc;
   return refresh_norms<T>(E);
+}
+
+// ---------------------------------------------------------------------------
+// row-partitioned engine: the pieces between the host-side allreduces (see include/pdlp_b200.h)
+// ---------------------------------------------------------------------------
+template <typename T>
+static int shard_kty(EngineT<T>* E, double* buf) {
+  pdlp_engine* B = E->base;
+  if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
+  SpmvOp<T, false> f{E->y, (T*)buf, E->S, 6};
+  CU(launch_stream(E->Kt, f, B->stream));
+  shard_tail_pack_kernel<<<1, 1, 0, B->stream>>>(E->S, buf + B->n);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n;
+  shard_rule_kernel<<<1, 1, 0, st>>>(E->S, buf + B->n);
+  if (save_prev) {
+    shard_primal_kernel<T, true><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
+                                                             E->ew_partials, E->ew_ticket);
+    DualOp<T, true, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    CU(launch_stream(E->K, d, st));
+    B->have_prev = true;
+  } else {
+    shard_primal_kernel<T, false><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
+                                                              E->ew_partials, E->ew_ticket);
+    DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    CU(launch_stream(E->K, d, st));
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int shard_check_begin(EngineT<T>* E, double* buf3) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int n = (int)B->n, m = (int)B->m;
+  if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
+  flush_kernel<T><<<ew_blocks(std::max(n, m), B->sms), 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, n, m,
+                                                                     E->S, B->have_prev ? 1 : 0);
+  CU(cudaGetLastError());
+  Spmv3Op<T> f{E->Y4, (T*)buf3};
+  CU(launch_stream(E->Kt, f, st));
+  return 0;
+}
+
+template <typename T>
+static int shard_check_mid(EngineT<T>* E, const double* buf3, double* buf9) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  shard_kkt_cols_kernel<T><<<E->ew_grid, 256, 0, st>>>(buf3, E->X4, E->c, E->l, E->u, B->scaled ? E->dcol : nullptr,
+                                                        (int)B->n, E->S, E->kkt_partials, E->ew_ticket);
+  KktRowsOp<T> b{E->X4, E->Y4, E->q, B->scaled ? E->drow : nullptr, E->S, 0};
+  CU(launch_stream(E->K, b, st));
+  shard_rows_pack_kernel<<<1, 1, 0, st>>>(E->S, buf9);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int shard_check_decide(EngineT<T>* E, const double* buf9, int force, double* buf1) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  shard_rows_unpack_kernel<<<1, 1, 0, st>>>(E->S, buf9);
+  decide_kernel<<<1, 1, 0, st>>>(E->S, force);
+  apply_restart_kernel<T><<<E->ew_grid, 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, E->xlast, E->ylast,
+                                                      (int)B->n, (int)B->m, E->S, E->ew_partials, E->ew_ticket);
+  shard_dy_pack_kernel<<<1, 1, 0, st>>>(E->S, buf1);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int shard_check_end(EngineT<T>* E, const double* buf1, pdlp_check* out) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  shard_dy_unpack_kernel<<<1, 1, 0, st>>>(E->S, buf1);
+  post_restart_kernel<<<1, 1, 0, st>>>(E->S, B->scaled ? 1 : 0);
+  CU(cudaGetLastError());
+  B->have_prev = false;
+  Scalars h;
+  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out) fill_check(out, h);
+  return 0;
 }
 
 template <typename T>
@@ -1108,6 +1202,62 @@ static int t_get_matrix_values(EngineT<T>* E, void* vals) {
 extern "C" int pdlp_get_matrix_values(pdlp_handle h, void* K_vals) {
   CHECK_HANDLE(h);
   return DISPATCH(h, t_get_matrix_values, K_vals);
+}
+
+extern "C" int pdlp_shard_enable(pdlp_handle h, double q_norm_global, double c_norm) {
+  CHECK_HANDLE(h);
+  if (h->dtype != PDLP_F64) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
+  Scalars s;
+  int rc = DISPATCH(h, t_get_scalars, &s);
+  if (rc) return rc;
+  s.sharded = 1; s.rule_pending = 0; s.q_norm = q_norm_global; s.c_norm = c_norm;
+  return DISPATCH(h, t_put_scalars, &s);
+}
+extern "C" int pdlp_shard_kty(pdlp_handle h, double* buf) {
+  CHECK_HANDLE(h);
+  if (!buf) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_kty, buf);
+}
+extern "C" int pdlp_shard_step(pdlp_handle h, const double* buf, int save_previous) {
+  CHECK_HANDLE(h);
+  if (!buf) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_step, buf, save_previous);
+}
+extern "C" int pdlp_shard_rule_pack(pdlp_handle h, double* buf4) {
+  CHECK_HANDLE(h);
+  if (!buf4) return fail(PDLP_ERR_INVALID, "null argument");
+  Scalars* S = h->dtype == PDLP_F64 ? ((EngineT<double>*)h->impl)->S : ((EngineT<float>*)h->impl)->S;
+  shard_tail_pack_kernel<<<1, 1, 0, h->stream>>>(S, buf4);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int pdlp_shard_rule_apply(pdlp_handle h, const double* buf4) {
+  CHECK_HANDLE(h);
+  if (!buf4) return fail(PDLP_ERR_INVALID, "null argument");
+  Scalars* S = h->dtype == PDLP_F64 ? ((EngineT<double>*)h->impl)->S : ((EngineT<float>*)h->impl)->S;
+  shard_rule_kernel<<<1, 1, 0, h->stream>>>(S, buf4);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int pdlp_shard_check_begin(pdlp_handle h, double* buf3) {
+  CHECK_HANDLE(h);
+  if (!buf3) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_check_begin, buf3);
+}
+extern "C" int pdlp_shard_check_mid(pdlp_handle h, const double* buf3, double* buf9) {
+  CHECK_HANDLE(h);
+  if (!buf3 || !buf9) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_check_mid, buf3, buf9);
+}
+extern "C" int pdlp_shard_check_decide(pdlp_handle h, const double* buf9, int force, double* buf1) {
+  CHECK_HANDLE(h);
+  if (!buf9 || !buf1) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_check_decide, buf9, force, buf1);
+}
+extern "C" int pdlp_shard_check_end(pdlp_handle h, const double* buf1, pdlp_check* host_out) {
+  CHECK_HANDLE(h);
+  if (!buf1) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, shard_check_end, buf1, host_out);
 }
 
 extern "C" int pdlp_primal_objective(pdlp_handle h, double* host_out) {

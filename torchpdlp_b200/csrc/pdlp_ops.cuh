@@ -39,7 +39,9 @@ struct Scalars {
   long long k;
   int t, n_restarts, adaptive, primal_update;
   int infeas_detect, infeas, infeas_k, solved;
-  int stop, m_ineq, pad0, pad1;
+  int stop, m_ineq;
+  int sharded;        // row-partitioned engine: sums over rows are partial until the host allreduces them
+  int rule_pending;   // sharded: the step rule of the latest iteration waits for the allreduced norms
   // restart check
   double sums[3][S_NSUM];
   int chk_kind, chk_use_avg, chk_t, chk_solved;
@@ -67,6 +69,38 @@ __device__ __forceinline__ Pair<float> ldg(const Pair<float>* p) {
 }
 
 template <typename T> __device__ __forceinline__ T clampv(T v, T lo, T hi) { return fmin(fmax(v, lo), hi); }
+
+// The step-size rule: step.py:96-115 (adaptive) / :40 (fixed).  Increments k (pdlp :76 counts the iteration
+// before the rule reads it) and returns the averaging weight of the new iterate and the next step size.
+__device__ inline void step_rule(Scalars& s, double dx2, double dy2, double inter, double& w, double& next) {
+  const long long k = s.k + 1;
+  s.k = k;
+  const double eta = s.eta, omega = s.omega;
+  w = eta;
+  next = eta;
+  if (s.adaptive) {
+    const double den = 2.0 * inter;
+    double eta_bar, t1;
+    if (den != 0.0) {
+      eta_bar = (omega * dx2 + dy2 / omega) / fabs(den);
+      t1 = (1.0 - pow((double)(k + 1), -0.3)) * eta_bar;
+    } else {
+      eta_bar = INFINITY;
+      t1 = INFINITY;
+    }
+    const double t2 = (1.0 + pow((double)(k + 1), -0.6)) * eta;
+    const double ep = fmin(t1, t2);
+    if (eta <= eta_bar) { w = eta; next = ep; } else { w = ep; next = ep; }
+  }
+}
+// averaging bookkeeping of pdlp :104-112 (the weight is folded into the sums by the next kernels that read the iterate)
+__device__ inline void commit_step(Scalars& s, double w, double next) {
+  s.eta_sum += w;
+  s.w_pending = w;
+  s.last_weight = w;
+  s.eta = next;
+  s.t += 1;
+}
 
 struct NoCtx {};
 
@@ -214,41 +248,25 @@ struct DualOp {
     Scalars& s = *S;
     s.dy2 = tot[0];
     s.inter = tot[1];
-    const long long k = s.k + 1;
-    s.k = k;
-    const double eta = s.eta, omega = s.omega;
-    double w = eta, next = eta;
-    if (s.adaptive) {
-      const double den = 2.0 * tot[1];
-      double eta_bar, t1;
-      if (den != 0.0) {
-        eta_bar = (omega * s.dx2 + tot[0] / omega) / fabs(den);
-        t1 = (1.0 - pow((double)(k + 1), -0.3)) * eta_bar;
-      } else {
-        eta_bar = INFINITY;
-        t1 = INFINITY;
-      }
-      const double t2 = (1.0 + pow((double)(k + 1), -0.6)) * eta;
-      const double ep = fmin(t1, t2);
-      if (eta <= eta_bar) { w = eta; next = ep; } else { w = ep; next = ep; }
+    if (s.sharded) {          // partial sums: the rule runs after the host allreduce (shard_rule_kernel)
+      s.rule_pending = 1;
+      return;
     }
+    double w, next;
+    step_rule(s, s.dx2, tot[0], tot[1], w, next);
     if (INFEAS) {
       s.inf_eq2 = tot[2]; s.inf_ineq_viol = tot[3]; s.inf_qtdy = tot[4]; s.inf_dy_viol = tot[5];
       // dual infeasibility test, enhancements.py:116-141 (only from the second iteration on, pdlp :89)
-      if (k > 1 && sqrt(tot[2]) < s.infeas_tol && tot[3] == 0.0 && s.inf_ctdx < s.infeas_tol &&
+      if (s.k > 1 && sqrt(tot[2]) < s.infeas_tol && tot[3] == 0.0 && s.inf_ctdx < s.infeas_tol &&
           s.inf_bound_viol == 0.0) {
         s.infeas = 1;
-        s.infeas_k = (int)k;
+        s.infeas_k = (int)s.k;
         s.stop = 1;
         s.last_weight = w;
         return;   // the reference returns before the averaging update (:94-100)
       }
     }
-    s.eta_sum += w;
-    s.w_pending = w;
-    s.last_weight = w;
-    s.eta = next;
-    s.t += 1;
+    commit_step(s, w, next);
   }
 };
 
@@ -411,6 +429,187 @@ struct KktRowsOp {
     }
   }
 };
+
+// ---------------------------------------------------------------------------
+// Row-partitioned (multi-GPU) pieces: SURVEY.md section 8e.  K^T y = sum over ranks of K_g^T y_g, so the column
+// side splits into "partial SpMV -> allreduce (host, NCCL) -> element-wise epilogue".
+// ---------------------------------------------------------------------------
+// out3[3 row + v] = (K_g^T Y4)[row][v] for the three iterates of the restart test
+template <typename T>
+struct Spmv3Op {
+  using value_type = T;
+  using Gather = Quad<T>;
+  using Ctx = NoCtx;
+  static constexpr int NV = 3;
+  static constexpr int NRED = 0;
+  static constexpr int UDIV = 2;
+  const Quad<T>* Y4;
+  T* out3;
+  __device__ bool begin() { return true; }
+  __device__ Quad<T> gather(int col) const { return Y4[col]; }
+  __device__ void mac(T (&acc)[3], T a, const Quad<T>& g) const {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) acc[v] += a * g.v[v];
+  }
+  __device__ Ctx row_load(int) const { return Ctx{}; }
+  __device__ void row_finish(int r, const Ctx&, const T (&acc)[3], double (&)[1]) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out3[3 * (size_t)r + v] = acc[v];
+  }
+  __device__ void finalize(const double (&)[1]) {}
+};
+
+// tail[0..1] = this rank's partial ||dy||^2, dy^T K dx of the latest iteration (0 when none is pending)
+__global__ void shard_tail_pack_kernel(const Scalars* S, double* tail) {
+  tail[0] = S->rule_pending ? S->dy2 : 0.0;
+  tail[1] = S->rule_pending ? S->inter : 0.0;
+  tail[2] = 0.0;
+  tail[3] = 0.0;
+}
+// after the allreduce: the step rule of the pending iteration with the global norms
+__global__ void shard_rule_kernel(Scalars* S, const double* tail) {
+  Scalars& s = *S;
+  if (!s.rule_pending) return;
+  s.dy2 = tail[0];
+  s.inter = tail[1];
+  double w, next;
+  step_rule(s, s.dx2, tail[0], tail[1], w, next);
+  commit_step(s, w, next);
+  s.rule_pending = 0;
+}
+
+// element-wise K1 epilogue on the allreduced K^T y (same arithmetic as PrimalOp::row_finish)
+template <typename T, bool SAVE_PREV>
+__global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
+                                    Quad<T>* X4, int n, Scalars* S, double* partials, unsigned int* ticket) {
+  if (S->stop) return;
+  const T tau = (T)(S->eta / S->omega);
+  const T wpend = (T)S->w_pending;
+  const int stride = gridDim.x * blockDim.x;
+  double dx2 = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T g = c[j] - (T)kty[j];
+    const T xo = xp[j].a;
+    const T xn = clampv(xo - tau * g, l[j], u[j]);
+    const T dx = xn - xo;
+    xp[j] = Pair<T>{xn, dx};
+    xsum[j] += wpend * xo;
+    if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
+    dx2 += (double)dx * (double)dx;
+  }
+  __shared__ double sh[32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+  if (lane == 0) sh[warp] = dx2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+    partials[blockIdx.x] = a;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&partials[b]);
+    S->dx2 = a;
+    *ticket = 0u;
+  }
+}
+
+// element-wise KKT column side on the allreduced K^T Y4 (same arithmetic as KktColsOp::row_finish); one block
+// per slab, fixed-order reduction of the 15 sums
+template <typename T>
+__global__ void shard_kkt_cols_kernel(const double* kty3, const Quad<T>* X4, const T* c, const T* l, const T* u,
+                                      const T* dcol, int n, Scalars* S, double* partials, unsigned int* ticket) {
+  double red[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) red[i] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const T cj = c[j], lj = l[j], uj = u[j];
+    const bool lo_inf = isinf(lj) && lj < T(0);
+    const bool up_inf = isinf(uj) && uj > T(0);
+    const T ld = lo_inf ? T(0) : lj;
+    const T ud = up_inf ? T(0) : uj;
+    const T inv = dcol ? T(1) / dcol[j] : T(1);
+    const Quad<T> x = X4[j];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const T g = cj - (T)kty3[3 * (size_t)j + v];
+      T lam;
+      if (lo_inf && up_inf) lam = T(0);
+      else if (lo_inf) lam = fmin(g, T(0));
+      else if (up_inf) lam = fmax(g, T(0));
+      else lam = g;
+      const T d = g - lam;
+      red[5 * v + 0] += (double)d * (double)d;
+      red[5 * v + 1] += (double)cj * (double)x.v[v];
+      red[5 * v + 2] += (double)ld * (double)fmax(lam, T(0));
+      red[5 * v + 3] += (double)ud * (double)fmin(lam, T(0));
+      const T du = d * inv;
+      red[5 * v + 4] += (double)du * (double)du;
+    }
+  }
+  __shared__ double sh[32][15];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 15; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) red[i] += __shfl_xor_sync(0xffffffffu, red[i], o);
+  }
+  if (lane == 0)
+    for (int i = 0; i < 15; ++i) sh[warp][i] = red[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 15; ++i) {
+      double a = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w][i];
+      partials[(size_t)blockIdx.x * 16 + i] = a;
+    }
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    for (int v = 0; v < 3; ++v) {
+      double t[5] = {0, 0, 0, 0, 0};
+      for (int b = 0; b < (int)gridDim.x; ++b)
+        for (int i = 0; i < 5; ++i) t[i] += __ldcg(&partials[(size_t)b * 16 + 5 * v + i]);
+      S->sums[v][S_DR2] = t[0];
+      S->sums[v][S_CTX] = t[1];
+      S->sums[v][S_LPOS] = t[2];
+      S->sums[v][S_UNEG] = t[3];
+      S->sums[v][S_DR2U] = t[4];
+    }
+    S->w_pending = 0.0;
+    *ticket = 0u;
+  }
+}
+
+// the row-side KKT sums (partial over this rank's rows) <-> a device buffer the host allreduces
+__global__ void shard_rows_pack_kernel(const Scalars* S, double* buf) {
+  for (int v = 0; v < 3; ++v) {
+    buf[3 * v + 0] = S->sums[v][S_PR2];
+    buf[3 * v + 1] = S->sums[v][S_QTY];
+    buf[3 * v + 2] = S->sums[v][S_PR2U];
+  }
+}
+__global__ void shard_rows_unpack_kernel(Scalars* S, const double* buf) {
+  for (int v = 0; v < 3; ++v) {
+    S->sums[v][S_PR2] = buf[3 * v + 0];
+    S->sums[v][S_QTY] = buf[3 * v + 1];
+    S->sums[v][S_PR2U] = buf[3 * v + 2];
+  }
+}
+__global__ void shard_dy_pack_kernel(const Scalars* S, double* buf) { buf[0] = S->restart_dy2; }
+__global__ void shard_dy_unpack_kernel(Scalars* S, const double* buf) { S->restart_dy2 = buf[0]; }
 
 // ---------------------------------------------------------------------------
 // scalar helpers

@@ -1,0 +1,205 @@
+"""Row-partitioned (multi-GPU) restarted PDHG: SURVEY.md section 8e.
+
+One process per GPU.  Rank g holds a contiguous block of rows K_g of K (and K_g^T),
+the matching slices of y, q and the dual sums; x, c, l, u are replicated.  K_g x is
+local; K^T y = sum_g K_g^T y_g is the single exchange of an iteration: one
+``all_reduce`` of n + 4 doubles (the 4 extra slots carry the partial ||dy||^2 and
+dy^T K dx of the previous iteration, so the adaptive step rule needs no second
+collective).  The reference has no distributed code; the semantics are those of its
+single-device loop (primal_dual_hybrid_gradient.py:54-177), which the sharded run
+reproduces up to the summation order of the allreduce.
+
+The collectives are issued by the host through ``torch.distributed`` (NCCL over
+NVLink on GPUs, gloo in the CPU tests); the device work between them goes through
+the ``pdlp_shard_*`` entry points of the C ABI.  ``prims`` abstracts those entry
+points so the orchestration below can be exercised on CPU with a test double
+(tests/fake_shard_prims.py) -- the product path always uses :class:`GpuShardPrims`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import Check, check
+
+
+def partition_rows(indptr: np.ndarray, parts: int, row_cost: float = 6.0) -> np.ndarray:
+    """Contiguous row blocks balanced by nnz + row_cost * rows.  Returns parts + 1 boundaries."""
+    m = len(indptr) - 1
+    weight = indptr.astype(np.float64) + row_cost * np.arange(m + 1)
+    targets = weight[-1] * np.arange(1, parts) / parts
+    cuts = np.searchsorted(weight, targets, side="left")
+    return np.concatenate([[0], cuts, [m]]).astype(np.int64)
+
+
+class GpuShardPrims:
+    """The C-ABI calls of one rank (a thin veneer over :class:`Engine`)."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.lib = engine.lib
+        self.h = engine.h
+        self.device = engine.device
+        self.n, self.m_local = engine.n, engine.m
+
+    def buffer(self, length):
+        return torch.zeros(length, dtype=torch.float64, device=self.device)
+
+    def enable(self, q_norm, c_norm):
+        check(self.lib.pdlp_shard_enable(self.h, float(q_norm), float(c_norm)))
+
+    def local_q_sumsq(self):
+        st = self.e.state()
+        return st.q_norm ** 2, st.c_norm
+
+    def spmv(self, v, transpose):
+        return self.e.spmv(v, transpose).to(torch.float64)
+
+    def kty(self, buf):
+        check(self.lib.pdlp_shard_kty(self.h, buf.data_ptr()))
+
+    def step(self, buf, save_previous):
+        check(self.lib.pdlp_shard_step(self.h, buf.data_ptr(), int(bool(save_previous))))
+
+    def rule_pack(self, buf4):
+        check(self.lib.pdlp_shard_rule_pack(self.h, buf4.data_ptr()))
+
+    def rule_apply(self, buf4):
+        check(self.lib.pdlp_shard_rule_apply(self.h, buf4.data_ptr()))
+
+    def check_begin(self, buf3):
+        check(self.lib.pdlp_shard_check_begin(self.h, buf3.data_ptr()))
+
+    def check_mid(self, buf3, buf9):
+        check(self.lib.pdlp_shard_check_mid(self.h, buf3.data_ptr(), buf9.data_ptr()))
+
+    def check_decide(self, buf9, force, buf1):
+        check(self.lib.pdlp_shard_check_decide(self.h, buf9.data_ptr(), int(bool(force)), buf1.data_ptr()))
+
+    def check_end(self, buf1):
+        chk = Check()
+        check(self.lib.pdlp_shard_check_end(self.h, buf1.data_ptr(), C.byref(chk)))
+        return chk
+
+    def set_iterate(self, x, y_local):
+        self.e.set_iterate(x, y_local)
+
+    def get_iterate(self):
+        return self.e.get_iterate()
+
+    def set_step(self, eta, omega, theta, adaptive):
+        self.e.set_step(eta, omega, theta, adaptive)
+
+    def set_options(self, tol, primal_update):
+        self.e.set_options(tol, primal_update, False, 1e-4)
+
+    def set_counters(self, k, t):
+        self.e.set_counters(k, t)
+
+    def state(self):
+        return self.e.state()
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+
+class ShardedSolver:
+    """Drives one rank of the row-partitioned solve.  Exposes the three calls the restart loop needs
+    (``iterate``, ``restart_check``, ``state``), so ``primal_dual_hybrid_gradient.run_restart_loop`` is shared
+    with the single-GPU path."""
+
+    def __init__(self, prims, group=None):
+        self.p = prims
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = prims.n
+        self.buf = prims.buffer(n + 4)
+        self.buf3 = prims.buffer(3 * n)
+        self.buf9 = prims.buffer(9)
+        self.buf4 = prims.buffer(4)
+        self.buf1 = prims.buffer(1)
+        self.collectives = 0
+        q2, c_norm = prims.local_q_sumsq()
+        t = torch.tensor([q2], dtype=torch.float64, device=self.buf.device)
+        self._allreduce(t)
+        self.q_norm, self.c_norm = float(t.item()) ** 0.5, c_norm
+        prims.enable(self.q_norm, self.c_norm)
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self.collectives += 1
+
+    # -- setup: power iteration on K^T K (helpers.py:41-51), start vector replicated ----------------
+    def power_iteration(self, b0, iters: int) -> float:
+        b = torch.as_tensor(b0, dtype=torch.float64).reshape(-1).to(self.buf.device)
+        for _ in range(iters):
+            v = self.p.spmv(self.p.spmv(b, False), True)        # K_g^T (K_g b): partial of K^T K b
+            self._allreduce(v)
+            b = v / torch.linalg.norm(v)
+        w = self.p.spmv(b, False)
+        s = torch.sum(w * w).reshape(1)
+        self._allreduce(s)
+        return float(s.item()) ** 0.5
+
+    def initial_step(self, power_iters=100, b0=None):
+        if b0 is None:
+            b0 = torch.randn(self.p.n, 1, dtype=torch.float64)     # same draw on every rank (same seed)
+        sigma = self.power_iteration(b0, power_iters)
+        eta = (1.0 / sigma) * 0.9
+        omega = self.c_norm / self.q_norm if (self.q_norm > 1e-6 and self.c_norm > 1e-6) else 1.0
+        return eta, omega, sigma
+
+    # -- the three calls of the restart loop --------------------------------------------------------
+    def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = False):
+        for i in range(n_iters):
+            self.p.kty(self.buf)
+            self._allreduce(self.buf)                              # THE exchange: n + 4 doubles
+            self.p.step(self.buf, save_previous and i == n_iters - 1)
+
+    def restart_check(self, force: bool = False):
+        self.p.rule_pack(self.buf4)                                # step rule of the block's last iteration
+        self._allreduce(self.buf4)
+        self.p.rule_apply(self.buf4)
+        self.p.check_begin(self.buf3)
+        self._allreduce(self.buf3)                                 # K^T y of current / average / previous iterate
+        self.p.check_mid(self.buf3, self.buf9)
+        self._allreduce(self.buf9)                                 # row-side KKT sums
+        self.p.check_decide(self.buf9, force, self.buf1)
+        self._allreduce(self.buf1)                                 # ||y_restart - y_last||^2
+        return self.p.check_end(self.buf1)
+
+    def state(self):
+        return self.p.state()
+
+    def primal_objective(self):
+        raise NotImplementedError("infeasibility detection is not available in the sharded engine")
+
+    # -- whole solve ----------------------------------------------------------------------------------
+    def solve(self, max_kkt=100_000, tol=1e-4, restart_period=40, primal_update=False, adaptive=False,
+              time_limit=3600.0, verbose=False, power_iters=100, b0=None, x_init=None, y_init_local=None):
+        from .primal_dual_hybrid_gradient import run_restart_loop
+        t0 = time.time()
+        eta, omega, sigma = self.initial_step(power_iters, b0)
+        self.p.set_iterate(x_init, y_init_local)
+        self.p.set_counters(0, 0)
+        self.p.set_step(eta, omega, 1.0, adaptive)
+        self.p.set_options(tol, primal_update)
+        self.p.enable(self.q_norm, self.c_norm)
+        rank0 = (not dist.is_initialized()) or dist.get_rank(self.group) == 0
+        prim_obj, k, n, j, status, trace = run_restart_loop(self, max_kkt, restart_period, time_limit, 0.0,
+                                                            verbose and rank0, False, use_graph=False, t_start=t0)
+        x, y_local = self.p.get_iterate()
+        return x, y_local, prim_obj, k, n, j, status, time.time() - t0, sigma
+
+
+def build_rank_engine(K_local, m_ineq_local: int, c, q_local, l, u, device=None):
+    """Engine on this rank's rows + the sharded driver."""
+    from .engine import Engine
+    eng = Engine(K_local, m_ineq_local, c, q_local, l, u, device=device, dtype=torch.float64)
+    return ShardedSolver(GpuShardPrims(eng))
