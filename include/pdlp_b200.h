@@ -190,6 +190,16 @@ int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u);
 /* Current (possibly scaled) values of K in the caller's CSR order (nnz values). */
 int pdlp_get_matrix_values(pdlp_handle h, void* K_vals);
 
+/* ---- fishnet start-point search (spectral_casting.py), 8 points per call -------------
+ * X8: n x 8 and Y8: m x 8 values, point index fastest (row j holds the 8 points' j-th entry,
+ * 64-byte aligned).  Fixed-step PDHG on all 8 points with one pass over K^T and one over K:
+ * PDHG_step (spectral_casting.py:254-293); Y8 = K X8 (:99); per point c^T x,
+ * l_dual^T max(lambda,0), u_dual^T min(lambda,0) of get_best_pts (:217-234) into
+ * host_out[3 v + {0,1,2}] (synchronises).  XB8 is an n x 8 scratch buffer.           */
+int pdlp_batch_spmv(pdlp_handle h, const void* X8, void* Y8);
+int pdlp_batch_step(pdlp_handle h, void* X8, void* XB8, void* Y8, double eta, double omega);
+int pdlp_batch_gap(pdlp_handle h, const void* X8, const void* Y8, double* host_out24);
+
 /* ---- row-partitioned engine (multi-GPU) ------------------
  * Each rank builds an ordinary handle on ITS rows of K (m = local rows, m_ineq = local
  * ">=" rows; n, c, l, u replicated) and marks it sharded.  K^T y = sum over ranks of the

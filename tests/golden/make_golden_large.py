@@ -28,7 +28,7 @@ CASES = {
     "cfg3": (lambda: synthetic.infeasible_lp(), [dict(infeasibility_detect=True),
                                                   dict(adaptive=True, primal_update=True, infeasibility_detect=True)]),
     "cfg4_small": (lambda: synthetic.powerlaw_rows_lp(160_000, 40_000, 400_000, max_nnz=20_000, name="cfg4_small"),
-                   [dict(adaptive=True, primal_update=True)]),
+                   [dict(max_kkt=3000), dict(adaptive=True, primal_update=True, max_kkt=3000)]),
 }
 
 

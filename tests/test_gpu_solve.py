@@ -182,3 +182,56 @@ def test_cfg2_ruiz_full_size_against_oracle():
     x, obj, k, n, j, status, secs, info = solve(lp, ruiz=True, adaptive=True, primal_weight=True)
     assert status == run["status"] and n == run["n"]
     assert abs(k - run["k"]) <= 40 and rel(obj, run["obj"]) < 2e-6, (k, run["k"], obj, run["obj"])
+
+
+FISH_RUNS = [r for r in load("cfg1_reference.json")["runs"] if r["options"]["fishnet"]]
+
+
+@pytest.mark.parametrize("run", FISH_RUNS, ids=lambda r: "-".join(k for k, v in r["options"].items() if v))
+def test_fishnet_against_executed_reference(run, cfg1):
+    """spectral_cast (32 points, 8 rounds of 32 batched PDHG steps, selection by signed gap, breeding) followed by
+    the warm-started solve, against the reference run with the same seed (CPU generator draws)."""
+    from torchpdlp_b200.enhancements import ruiz_precondition
+    from torchpdlp_b200.primal_dual_hybrid_gradient import pdlp_algorithm
+    from torchpdlp_b200.spectral_casting import spectral_cast
+    o, ref = run["options"], run["reference"]
+    torch.set_default_dtype(torch.float64)
+    c, K, q, m_ineq, l, u = cfg1.torch_tensors(layout="csr", device="cuda")
+    torch.manual_seed(0)
+    dt, used = None, 0.0
+    if o["ruiz"]:
+        K, c, q, l, u, dt, used = ruiz_precondition(c, K, q, l, u, device="cuda")
+    x0, y0 = spectral_cast(K, c, q, l, u, m_ineq, k=32, device="cuda")
+    assert x0.shape == (cfg1.n,) and y0.shape == (cfg1.m,)
+    x, obj, k, n, j, status, secs = pdlp_algorithm(K, m_ineq, c, q, l, u, "cuda", verbose=False, precondition=o["ruiz"],
+                                                   primal_update=o["primal_weight"], adaptive=o["adaptive"], data_precond=dt,
+                                                   time_used=used, x_init=x0, y_init=y0)
+    assert status == ref["status"] and n == ref["n"]
+    if o["adaptive"]:
+        assert abs(k - ref["k"]) <= 40 and rel(obj, ref["obj"]) < 2e-6, (k, ref["k"], obj, ref["obj"])
+    else:
+        assert (k, j) == (ref["k"], ref["j"]) and rel(obj, ref["obj"]) < 1e-8, (k, j, obj, ref)
+
+
+def test_console_entry_writes_reference_csv(tmp_path):
+    """python -m torchpdlp_b200.main on a folder of MPS files: same CSV schema and statuses as PDLP/main.py:142-172."""
+    import shutil
+    import pandas as pd
+    from scipy.optimize import linprog
+    from torchpdlp_b200.main import main
+    inst, outdir = tmp_path / "inst", tmp_path / "out"
+    inst.mkdir()
+    shutil.copy(os.path.join(GOLD, "small_generated.mps"), inst / "a.mps")
+    shutil.copy(os.path.join(GOLD, "small_handwritten.mps"), inst / "b.mps")
+    (inst / "broken.mps").write_text("ROWS\n Q nonsense extra tokens\n")
+    res = main(["--instance_path", str(inst), "--output_path", str(outdir), "--adaptive_stepsize", "--primal_weight_update",
+                "--precondition", "--tolerance", "1e-6"])
+    df = pd.read_csv(outdir / "solver_results.csv")
+    assert list(df.columns) == ["File", "Objective", "Iterations (k)", "Restarts (n)", "KKT Passes (j)", "Time (s)", "Status"]
+    assert list(df["File"]) == ["a.mps", "b.mps", "broken.mps"]
+    assert df["Status"][0] == "Solved"
+    lp = synthetic.feasible_lp(40, 20, 8, 0.2, seed=5)
+    G, A = -lp.K[:lp.m_ineq], lp.K[lp.m_ineq:]
+    ref = linprog(lp.c, A_ub=G, b_ub=-lp.q[:lp.m_ineq], A_eq=A, b_eq=lp.q[lp.m_ineq:], bounds=list(zip(lp.l, lp.u)), method="highs")
+    assert abs(float(df["Objective"][0]) - ref.fun) <= 1e-3 * max(1.0, abs(ref.fun))
+    assert str(df["Status"][2]).startswith(("Failed to load", "Solver failed")) or "unpack" in str(df["Status"][2])

@@ -79,6 +79,9 @@ SYMBOLS = {
     "pdlp_set_scaling": (_I, [_P, _P, _P]),
     "pdlp_get_problem": (_I, [_P, _P, _P, _P, _P]),
     "pdlp_get_matrix_values": (_I, [_P, _P]),
+    "pdlp_batch_spmv": (_I, [_P, _P, _P]),
+    "pdlp_batch_step": (_I, [_P, _P, _P, _P, _D, _D]),
+    "pdlp_batch_gap": (_I, [_P, _P, _P, C.POINTER(_D)]),
     "pdlp_shard_enable": (_I, [_P, _D, _D]),
     "pdlp_shard_kty": (_I, [_P, _P]),
     "pdlp_shard_step": (_I, [_P, _P, _I]),

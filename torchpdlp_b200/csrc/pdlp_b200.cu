@@ -736,6 +736,34 @@ static int engine_pock_chambolle(EngineT<T>* E) {
 }
 
 // ---------------------------------------------------------------------------
+// fishnet batches (8 right-hand sides per pass over the matrix)
+// ---------------------------------------------------------------------------
+template <typename T>
+static int batch_spmv(EngineT<T>* E, const void* X8, void* Y8) {
+  BatchOp<T, 0> f{(const Oct<T>*)X8, (Oct<T>*)Y8, nullptr, nullptr, nullptr, nullptr, T(0), 0};
+  CU(launch_stream(E->K, f, E->base->stream));
+  return 0;
+}
+template <typename T>
+static int batch_step(EngineT<T>* E, void* X8, void* XB8, void* Y8, double eta, double omega) {
+  cudaStream_t st = E->base->stream;
+  BatchOp<T, 1> p{(const Oct<T>*)Y8, (Oct<T>*)X8, (Oct<T>*)XB8, E->c, E->l, E->u, (T)(eta / omega), 0};
+  CU(launch_stream(E->Kt, p, st));
+  BatchOp<T, 2> d{(const Oct<T>*)XB8, (Oct<T>*)Y8, nullptr, E->q, nullptr, nullptr, (T)(eta * omega), (int)E->base->m_ineq};
+  CU(launch_stream(E->K, d, st));
+  return 0;
+}
+template <typename T>
+static int batch_gap(EngineT<T>* E, const void* X8, const void* Y8, double* out24) {
+  cudaStream_t st = E->base->stream;
+  BatchGapOp<T> g{(const Oct<T>*)Y8, (const Oct<T>*)X8, E->c, E->l, E->u, E->S};
+  CU(launch_stream(E->Kt, g, st));
+  CU(cudaMemcpyAsync(out24, (char*)E->S + offsetof(Scalars, batch), 24 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // row-partitioned engine: the pieces between the host-side allreduces (see include/pdlp_b200.h)
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -1202,6 +1230,22 @@ static int t_get_matrix_values(EngineT<T>* E, void* vals) {
 extern "C" int pdlp_get_matrix_values(pdlp_handle h, void* K_vals) {
   CHECK_HANDLE(h);
   return DISPATCH(h, t_get_matrix_values, K_vals);
+}
+
+extern "C" int pdlp_batch_spmv(pdlp_handle h, const void* X8, void* Y8) {
+  CHECK_HANDLE(h);
+  if (!X8 || !Y8) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, batch_spmv, X8, Y8);
+}
+extern "C" int pdlp_batch_step(pdlp_handle h, void* X8, void* XB8, void* Y8, double eta, double omega) {
+  CHECK_HANDLE(h);
+  if (!X8 || !XB8 || !Y8) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, batch_step, X8, XB8, Y8, eta, omega);
+}
+extern "C" int pdlp_batch_gap(pdlp_handle h, const void* X8, const void* Y8, double* host_out24) {
+  CHECK_HANDLE(h);
+  if (!X8 || !Y8 || !host_out24) return fail(PDLP_ERR_INVALID, "null argument");
+  return DISPATCH(h, batch_gap, X8, Y8, host_out24);
 }
 
 extern "C" int pdlp_shard_enable(pdlp_handle h, double q_norm_global, double c_norm) {

@@ -21,6 +21,10 @@ template <> struct __align__(8) Pair<float> { float a, b; };
 template <typename T> struct __align__(32) Quad { T v[4]; };
 template <> struct __align__(16) Quad<float> { float v[4]; };
 
+// 8 right-hand sides side by side (fishnet batches, spectral_casting.py:254-293)
+template <typename T> struct __align__(64) Oct { T v[8]; };
+template <> struct __align__(32) Oct<float> { float v[8]; };
+
 // slots of Quad: the three iterates the restart test evaluates (:121-126)
 enum { IT_CUR = 0, IT_AVG = 1, IT_PREV = 2 };
 
@@ -55,6 +59,8 @@ struct Scalars {
   double inf_dres2, inf_lsum, inf_usum;
   // scratch reductions: power iteration, Ruiz, norms
   double scratch[8];
+  // fishnet: per point c^T x, l_dual^T max(lam,0), u_dual^T min(lam,0) for a batch of 8 points
+  double batch[24];
 };
 
 template <typename T>
@@ -427,6 +433,115 @@ struct KktRowsOp {
       S->sums[v][S_QTY] = tot[3 * v + 1];
       S->sums[v][S_PR2U] = tot[3 * v + 2];
     }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Fishnet ("spectral casting", spectral_casting.py): fixed-step PDHG on 8 points at once.  The matrix is
+// streamed once per 8 right-hand sides; a gather brings the 8 values of a column (64 contiguous bytes).
+// ---------------------------------------------------------------------------
+// MODE 0: Y8 = K X8 (spectral_casting.py:99).  MODE 1 (rows of K^T): X8 <- clip(X8 - tau (c - K^T Y8)), XB8 = 2 X8' - X8
+// (:272-281).  MODE 2 (rows of K): Y8 <- proj(Y8 + sigma (q - K XB8)) (:285-291).
+template <typename T, int MODE>
+struct BatchOp {
+  using value_type = T;
+  using Gather = Oct<T>;
+  struct Ctx { T a, b, c; };
+  static constexpr int NV = 8;
+  static constexpr int NRED = 0;
+  static constexpr int UDIV = 4;
+  const Oct<T>* in;      // gathered operand
+  Oct<T>* out;           // MODE 0: Y8; MODE 1: X8 (updated in place); MODE 2: Y8 (in place)
+  Oct<T>* aux;           // MODE 1: XB8
+  const T* v0;           // MODE 1: c; MODE 2: q
+  const T* v1;           // MODE 1: l
+  const T* v2;           // MODE 1: u
+  T step;                // tau or sigma
+  int m_ineq;
+  __device__ bool begin() { return true; }
+  __device__ Oct<T> gather(int col) const { return in[col]; }
+  __device__ void mac(T (&acc)[8], T a, const Oct<T>& g) const {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] += a * g.v[v];
+  }
+  __device__ Ctx row_load(int r) const {
+    if (MODE == 1) return Ctx{v0[r], v1[r], v2[r]};
+    if (MODE == 2) return Ctx{v0[r], T(0), T(0)};
+    return Ctx{T(0), T(0), T(0)};
+  }
+  __device__ void row_finish(int r, const Ctx& k, const T (&acc)[8], double (&)[1]) {
+    Oct<T> o;
+    if (MODE == 0) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) o.v[v] = acc[v];
+      out[r] = o;
+    } else if (MODE == 1) {
+      const Oct<T> xo = out[r];
+      Oct<T> xb;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const T xn = clampv(xo.v[v] - step * (k.a - acc[v]), k.b, k.c);
+        o.v[v] = xn;
+        xb.v[v] = T(2) * xn - xo.v[v];
+      }
+      out[r] = o;
+      aux[r] = xb;
+    } else {
+      const Oct<T> yo = out[r];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        T yn = yo.v[v] + step * (k.a - acc[v]);
+        if (r < m_ineq) yn = fmax(yn, T(0));
+        o.v[v] = yn;
+      }
+      out[r] = o;
+    }
+  }
+  __device__ void finalize(const double (&)[1]) {}
+};
+
+// signed duality-gap terms of 8 points (spectral_casting.py:217-234): rows of K^T, gathers Y8
+template <typename T>
+struct BatchGapOp {
+  using value_type = T;
+  using Gather = Oct<T>;
+  struct Ctx { T c, l, u; Oct<T> x; };
+  static constexpr int NV = 8;
+  static constexpr int NRED = 24;
+  static constexpr int UDIV = 4;
+  const Oct<T>* Y8;
+  const Oct<T>* X8;
+  const T* c;
+  const T* l;
+  const T* u;
+  Scalars* S;
+  __device__ bool begin() { return true; }
+  __device__ Oct<T> gather(int col) const { return Y8[col]; }
+  __device__ void mac(T (&acc)[8], T a, const Oct<T>& g) const {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] += a * g.v[v];
+  }
+  __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], X8[j]}; }
+  __device__ void row_finish(int, const Ctx& k, const T (&acc)[8], double (&red)[24]) {
+    const bool lo_inf = isinf(k.l) && k.l < T(0);
+    const bool up_inf = isinf(k.u) && k.u > T(0);
+    const T ld = lo_inf ? T(0) : k.l;
+    const T ud = up_inf ? T(0) : k.u;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const T g = k.c - acc[v];
+      T lam;
+      if (lo_inf && up_inf) lam = T(0);
+      else if (lo_inf) lam = fmin(g, T(0));
+      else if (up_inf) lam = fmax(g, T(0));
+      else lam = g;
+      red[3 * v + 0] += (double)k.c * (double)k.x.v[v];
+      red[3 * v + 1] += (double)ld * (double)fmax(lam, T(0));
+      red[3 * v + 2] += (double)ud * (double)fmin(lam, T(0));
+    }
+  }
+  __device__ void finalize(const double (&tot)[24]) {
+    for (int i = 0; i < 24; ++i) S->batch[i] = tot[i];
   }
 };
 
