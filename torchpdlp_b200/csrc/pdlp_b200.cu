@@ -37,8 +37,6 @@ extern "C" const char* pdlp_last_error(void) { return g_err.c_str(); }
 // ---------------------------------------------------------------------------
 struct HostSell {
   std::vector<Piece> pieces;
-  std::vector<long long> slot_begin;   // first packed slot of each piece (+ total)
-  std::vector<int> src;                // packed slot -> CSR index, -1 = padding
   std::vector<int> perm;               // row per (slice, lane), -1 = padding lane
   std::vector<int> warp_begin;         // grid * W + 1
   std::vector<int> long_rows;
@@ -94,36 +92,17 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
       i = j + 1;
     }
   }
-  // block offsets and the slot -> CSR index map
+  // block offsets; the first step of a split slice's piece travels in the upper bits of flags (pack_kernel)
   const int np = (int)P.pieces.size();
-  P.slot_begin.resize(np + 1);
   size_t bytes = 0;
-  long long slots = 0;
   for (int p = 0; p < np; ++p) {
     Piece& pc = P.pieces[p];
     pc.data_off16 = (uint32_t)(bytes / 16);
-    P.slot_begin[p] = slots;
+    pc.flags |= (uint32_t)kbase[p] << 8;
     const long long steps = (long long)pc.klen * pc.nslices;
-    slots += steps * 32;
     bytes += 16 + ((pc.flags & PIECE_FIRST) ? (size_t)pc.nslices * 128 : 0) + (size_t)steps * 32 * (4 + value_bytes);
   }
-  P.slot_begin[np] = slots;
   P.packed_bytes = bytes;
-  P.src.assign((size_t)slots, -1);
-  for (int p = 0; p < np; ++p) {
-    const Piece& pc = P.pieces[p];
-    int* dst = P.src.data() + P.slot_begin[p];
-    for (int sl = 0; sl < pc.nslices; ++sl)
-      for (int r = 0; r < 32; ++r) {
-        const int row = P.perm[(size_t)pc.perm_off + sl * 32 + r];
-        if (row < 0) continue;
-        const int L = len(row), base = rowptr[row];
-        for (int k = 0; k < pc.klen; ++k) {
-          const int kk = kbase[p] + k;
-          if (kk < L) dst[((size_t)sl * pc.klen + k) * 32 + r] = base + kk;
-        }
-      }
-  }
   // warps: contiguous piece ranges balanced by bytes (+ a fixed per-piece cost), cut only where rows start
   std::vector<double> pre(np + 1, 0.0);
   for (int p = 0; p < np; ++p)
@@ -147,25 +126,39 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
   return P;
 }
 
-// fill the piece blocks: header, row ids, and packed[slot] <- CSR[src[slot]] (cols and vals); one CTA per piece
+// fill the piece blocks: header, row ids, and for every slot (slice sl, step k, lane r) the k-th entry of the
+// lane's row (column index and value), zero beyond the row's end; one CTA per piece
 template <typename T>
-__global__ void pack_kernel(const Piece* pieces, const long long* slot_begin, const int* src, const int* perm,
-                            int npieces, const int* colidx, const T* vals, unsigned char* packed) {
+__global__ void pack_kernel(const Piece* pieces, const int* perm, int npieces, const int* rowptr, const int* colidx,
+                            const T* vals, unsigned char* packed) {
   for (int p = blockIdx.x; p < npieces; p += gridDim.x) {
     const Piece pc = pieces[p];
     unsigned char* blk = packed + (size_t)pc.data_off16 * 16u;
-    const int nslots = (int)pc.klen * pc.nslices * 32;
+    const int klen = pc.klen;
+    const int nslots = klen * pc.nslices * 32;
     const int nrows = (pc.flags & PIECE_FIRST) ? (int)pc.nslices * 32 : 0;
-    if (threadIdx.x == 0) *reinterpret_cast<Piece*>(blk) = pc;
+    const int kbase = (int)(pc.flags >> 8);
+    if (threadIdx.x == 0) {
+      Piece hdr = pc;
+      hdr.flags &= 0xffu;
+      *reinterpret_cast<Piece*>(blk) = hdr;
+    }
     int* rdst = reinterpret_cast<int*>(blk + 16);
     for (int i = threadIdx.x; i < nrows; i += blockDim.x) rdst[i] = perm[pc.perm_off + i];
     int* cdst = rdst + nrows;
     T* vdst = reinterpret_cast<T*>(cdst + nslots);
-    const int* sp = src + slot_begin[p];
     for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
-      const int s = sp[i];
-      cdst[i] = s >= 0 ? colidx[s] : 0;
-      vdst[i] = s >= 0 ? vals[s] : T(0);
+      const int r = i & 31;
+      const int k = (i >> 5) % klen;
+      const int sl = (i >> 5) / klen;
+      const int row = perm[pc.perm_off + sl * 32 + r];
+      int src = -1;
+      if (row >= 0) {
+        const int b = rowptr[row], e = rowptr[row + 1];
+        if (b + kbase + k < e) src = b + kbase + k;
+      }
+      cdst[i] = src >= 0 ? colidx[src] : 0;
+      vdst[i] = src >= 0 ? vals[src] : T(0);
     }
   }
 }
@@ -182,8 +175,6 @@ struct DeviceCsr {
   // SELL-32-sigma packed copy (hot kernels)
   unsigned char* packed = nullptr;
   Piece* pieces = nullptr;
-  long long* slot_begin = nullptr;
-  int* src = nullptr;
   int* perm = nullptr;
   int* warp_begin = nullptr;
   int* long_rows = nullptr;
@@ -230,9 +221,11 @@ struct EngineT {
   std::vector<void*> allocs;
 };
 
+// stream-ordered allocation from the device's default pool (kept cached: building an engine right after another
+// one was destroyed does not go back to the driver)
 template <typename T>
 static int dev_alloc(EngineT<T>* E, void** p, size_t bytes) {
-  CU(cudaMalloc(p, bytes ? bytes : 16));
+  CU(cudaMallocAsync(p, bytes ? bytes : 16, E->base->stream));
   E->allocs.push_back(*p);
   return 0;
 }
@@ -270,8 +263,8 @@ template <typename T>
 static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
   pdlp_engine* B = E->base;
   if (A.npieces == 0) return 0;
-  pack_kernel<T><<<std::min(A.npieces, B->sms * 16), 256, 0, B->stream>>>(A.pieces, A.slot_begin, A.src, A.perm,
-                                                                         A.npieces, A.colidx, A.vals, A.packed);
+  pack_kernel<T><<<std::min(A.npieces, B->sms * 16), 256, 0, B->stream>>>(A.pieces, A.perm, A.npieces, A.rowptr,
+                                                                         A.colidx, A.vals, A.packed);
   CU(cudaGetLastError());
   return 0;
 }
@@ -305,16 +298,12 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   A.packed_bytes = P.packed_bytes;
   ALLOC(A.packed, P.packed_bytes + 16);
   ALLOC(A.pieces, P.pieces.size() + 1);
-  ALLOC(A.slot_begin, P.slot_begin.size());
-  ALLOC(A.src, P.src.size() + 1);
   ALLOC(A.perm, P.perm.size() + 32);
   ALLOC(A.warp_begin, P.warp_begin.size());
   ALLOC(A.long_rows, P.long_rows.size() + 1);
   ALLOC(A.partials, (size_t)P.grid * MAX_RED);
   ALLOC(A.ticket, 1);
   CU(cudaMemcpyAsync(A.pieces, P.pieces.data(), sizeof(Piece) * P.pieces.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A.slot_begin, P.slot_begin.data(), sizeof(long long) * P.slot_begin.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A.src, P.src.data(), sizeof(int) * P.src.size(), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(A.perm, P.perm.data(), sizeof(int) * P.perm.size(), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(A.warp_begin, P.warp_begin.data(), sizeof(int) * P.warp_begin.size(), cudaMemcpyHostToDevice, st));
   if (!P.long_rows.empty())
@@ -391,7 +380,8 @@ static void engine_destroy(pdlp_engine* B) {
   EngineT<T>* E = (EngineT<T>*)B->impl;
   if (!E) return;
   for (auto& g : E->graphs) cudaGraphExecDestroy(g.exec);
-  for (void* p : E->allocs) cudaFree(p);
+  for (void* p : E->allocs) cudaFreeAsync(p, B->stream);
+  cudaStreamSynchronize(B->stream);
   delete E;
   B->impl = nullptr;
 }
@@ -994,6 +984,12 @@ extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, in
   B->dtype = dtype; B->device = dev; B->stream = (cudaStream_t)stream;
   B->m = m; B->n = n; B->m_ineq = m_ineq; B->nnz = nnz;
   B->sms = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   int rc = dtype == PDLP_F64
                ? engine_create<double>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u)
                : engine_create<float>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u);
