@@ -184,3 +184,41 @@ def test_bitwise_reproducible(cfg1):
         outs.append((x.cpu(), y.cpu(), eng.state().eta))
         eng.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_fp32_engine_matches_fp32_oracle(cfg1):
+    """The reference's MPS path is float32 (util.py:240-246): the fp32 instantiation of every kernel, against the
+    oracle run in float32 (tolerances at float32 resolution)."""
+    torch.set_default_dtype(torch.float32)
+    try:
+        lp = cfg1
+        f32 = lambda v: torch.from_numpy(np.asarray(v, dtype=np.float32))
+        import scipy.sparse as sp
+        K32 = sp.csr_matrix((lp.K.data.astype(np.float32), lp.K.indices, lp.K.indptr), shape=lp.K.shape)
+        op = orc.Operator(K32, backend="scipy")
+        c, q, l, u = f32(lp.c), f32(lp.q), f32(lp.l), f32(lp.u)
+        g = torch.Generator().manual_seed(3)
+        x = torch.rand(lp.n, generator=g) * 2 - 1
+        y = torch.randn(lp.m, generator=g).abs()
+        eng = make_engine(lp, dtype=torch.float32)
+        ox, oy, ow, on = orc.adaptive_one_step_pdhg(x, y, c, q, op, l, u, lp.m_ineq, 0.05, 1.3, 1.0, 5)
+        eng.set_iterate(x, y)
+        eng.set_step(0.05, 1.3, 1.0, adaptive=True)
+        eng.set_counters(4, 0)
+        eng.iterate(1, use_graph=False)
+        gx, gy = (t.cpu() for t in eng.get_iterate())
+        assert gx.dtype == torch.float32
+        assert float((gx - ox).abs().max()) <= 2e-5 * max(1.0, float(ox.abs().max()))
+        assert float((gy - oy).abs().max()) <= 2e-5 * max(1.0, float(oy.abs().max()))
+        st = eng.state()
+        assert abs(st.eta - float(on)) <= 1e-3 * abs(float(on))
+        # whole solve in fp32 reaches the same optimum to fp32-level accuracy
+        from torchpdlp_b200.primal_dual_hybrid_gradient import pdlp_algorithm
+        cc, K, qq, m_ineq, ll, uu = lp.torch_tensors(dtype=torch.float32, layout="csr", device="cuda")
+        torch.manual_seed(0)
+        xs, obj, k, n, j, status, secs = pdlp_algorithm(K, m_ineq, cc, qq, ll, uu, "cuda", verbose=False, adaptive=True)
+        assert status == "Solved" and xs.dtype == torch.float32
+        assert abs(obj - (-4273.2619)) <= 1e-3 * 4273.0
+        eng.close()
+    finally:
+        torch.set_default_dtype(torch.float64)

@@ -23,7 +23,7 @@
 namespace pdlp {
 
 #ifndef PDLP_W
-#define PDLP_W 16         // warps per CTA
+#define PDLP_W 12         // warps per CTA
 #endif
 #ifndef PDLP_S
 #define PDLP_S 2          // ring stages per warp
@@ -240,30 +240,54 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   }
 
   // ---------------- SELL pieces: one row per lane ----------------
+  // Software pipeline: while piece p is multiplied, reduced into its row and finished, the first batch of
+  // gathers of piece p + 1 is already in flight (g_nxt), so a lane keeps up to 2 U gathers outstanding.
   {
     T acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = T(0);
     typename Op::Ctx ctx;
     int row = -1;
+    typename Op::Gather g_cur[U], g_nxt[U];
+    auto stage_of = [&](int p) { return ring + (size_t)((p - pb) % Cfg::S) * Cfg::STAGE_BYTES; };
+    // first batch of a piece: slice 0, steps [0, min(U, klen))
+    auto issue_first = [&](int p, typename Op::Gather (&g)[U]) {
+      const int it = p - pb;
+      mbar_wait(&full_bar[warp][it % Cfg::S], (it / Cfg::S) & 1);
+      const unsigned char* st = stage_of(p);
+      const Piece d = *reinterpret_cast<const Piece*>(st);
+      const int* cols = reinterpret_cast<const int*>(st + 16) + ((d.flags & PIECE_FIRST) ? (int)d.nslices * 32 : 0);
+      const int klen = d.klen;
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (j < klen) g[j] = op.gather(PDLP_COL(cols[j * 32 + lane]));
+    };
+    if (pb < pe) issue_first(pb, g_cur);
     for (int p = pb; p < pe; ++p) {
       Piece d_refill = Piece{0, 0, 0, 0, 0};
       const bool refill = (p + Cfg::S < pe);
       if (refill && lane == 0) d_refill = A.pieces[p + Cfg::S];     // used after this piece: latency hidden
-      const int it = p - pb;
-      const int s = it % Cfg::S;
-      const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-      mbar_wait(&full_bar[warp][s], (it / Cfg::S) & 1);
-      const Piece d = *reinterpret_cast<const Piece*>(st);
+      const int s = (p - pb) % Cfg::S;
+      const unsigned char* st = stage_of(p);
+      const Piece d = *reinterpret_cast<const Piece*>(st);          // stage already waited for by issue_first
       const int klen = d.klen;
       const int nsl = d.nslices;
       const bool first = (d.flags & PIECE_FIRST) != 0;
       const int* rows = reinterpret_cast<const int*>(st + 16);
       const int* cols = rows + (first ? nsl * 32 : 0);
       const T* vals = reinterpret_cast<const T*>(cols + klen * nsl * 32);
+      if (first) {
+        row = rows[lane];
+#ifndef PDLP_DBG_NOEPI
+        if (row >= 0) ctx = op.row_load(row);
+#endif
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = T(0);
+      }
+      if (p + 1 < pe) issue_first(p + 1, g_nxt);                    // next piece's gathers fly during the work below
 #ifndef PDLP_DBG_NOWORK
       for (int sl = 0; sl < nsl; ++sl) {
-        if (first) {
+        if (sl > 0) {       // further complete slices packed into this piece
           row = rows[sl * 32 + lane];
 #ifndef PDLP_DBG_NOEPI
           if (row >= 0) ctx = op.row_load(row);
@@ -272,7 +296,14 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
           for (int v = 0; v < NV; ++v) acc[v] = T(0);
         }
         const int base = sl * klen;
-        for (int k0 = 0; k0 < klen; k0 += U) {
+        int k0 = 0;
+        if (sl == 0) {      // the pre-issued batch
+#pragma unroll
+          for (int j = 0; j < U; ++j)
+            if (j < klen) op.mac(acc, vals[j * 32 + lane], g_cur[j]);
+          k0 = U;
+        }
+        for (; k0 < klen; k0 += U) {
           typename Op::Gather g[U];
 #pragma unroll
           for (int j = 0; j < U; ++j)
@@ -295,6 +326,8 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
         tma_load_1d(ring + (size_t)s * Cfg::STAGE_BYTES, A.packed + (size_t)d_refill.data_off16 * 16u, bytes,
                     &full_bar[warp][s]);
       }
+#pragma unroll
+      for (int j = 0; j < U; ++j) g_cur[j] = g_nxt[j];
     }
   }
 
