@@ -320,16 +320,22 @@ def run_sharded(args, world, rank, local, dev):
         p.enable(solver.q_norm, solver.c_norm)
 
     def step():
-        solver.iterate(RESTART_PERIOD, save_previous=True)
+        solver.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
         return solver.restart_check(False)
 
     def barrier():
         dist.barrier(); torch.cuda.synchronize(dev)
 
+    def note(msg):
+        if os.environ.get("PDLP_BENCH_TRACE"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     reset()
+    note("warmup")
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    note("timed region")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -340,6 +346,7 @@ def run_sharded(args, world, rank, local, dev):
         step()
     e1.record()
     barrier()
+    note("timed region done")
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -349,10 +356,13 @@ def run_sharded(args, world, rank, local, dev):
     # e2e: whole sharded solve from host data (engine build on every rank + power iteration + solve)
     barrier()
     t0 = time.perf_counter()
+    note("e2e build")
     solver2 = build_rank_engine(Kb, mi, c, q, l, u, device=dev)
     torch.manual_seed(0)
+    note("e2e solve")
     x, y, obj, k, nres, j, status, secs, sig = solver2.solve(adaptive=True, primal_update=True, max_kkt=20_000)
     x_host = x.cpu()
+    note(f"e2e done {status} k={k}")
     barrier()
     e2e_s = time.perf_counter() - t0
     if rank == 0:
@@ -380,6 +390,11 @@ def run_sharded(args, world, rank, local, dev):
             "cpu_baseline": None,
         }
         print(json.dumps(out), flush=True)
+    # captured graphs hold NCCL work: drop them (and the engines) before the communicator goes away
+    solver.close()
+    solver2.close()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -121,6 +121,9 @@ int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ine
                 const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals,
                 const void* c, const void* q, const void* l, const void* u, void* stream);
 int pdlp_destroy(pdlp_handle h);
+/* Redirect the engine's work to another stream of the same device (e.g. the capture stream of a
+ * CUDA graph that also holds the NCCL allreduce of the sharded loop).  The caller orders the streams. */
+int pdlp_set_stream(pdlp_handle h, void* stream);
 
 /* ---- iterate / scalars ----------------------------------------------------
  * x_init / y_init of pdlp_algorithm (:31-36).  Also resets the averaging sums,
@@ -211,7 +214,7 @@ int pdlp_batch_gap(pdlp_handle h, const void* X8, const void* Y8, double* host_o
  *                 pdlp_shard_step(buf, save) step rule of the PREVIOUS iteration (global norms),
  *                                            primal update, local dual kernel
  *   restart test  pdlp_shard_rule_pack / allreduce(4) / pdlp_shard_rule_apply   (pending rule)
- *                 pdlp_shard_check_begin(buf3)   buf3[3j+v] = K_g^T Y_g for the 3 iterates
+ *                 pdlp_shard_check_begin(buf3, have_previous)   buf3[3j+v] = K_g^T Y_g for the 3 iterates
  *                 allreduce(buf3, 3n)
  *                 pdlp_shard_check_mid(buf3, buf9)   column sums (replicated), row sums (partial)
  *                 allreduce(buf9, 9)
@@ -224,7 +227,7 @@ int pdlp_shard_kty(pdlp_handle h, double* buf);
 int pdlp_shard_step(pdlp_handle h, const double* buf, int save_previous);
 int pdlp_shard_rule_pack(pdlp_handle h, double* buf4);
 int pdlp_shard_rule_apply(pdlp_handle h, const double* buf4);
-int pdlp_shard_check_begin(pdlp_handle h, double* buf3);
+int pdlp_shard_check_begin(pdlp_handle h, double* buf3, int have_previous);
 int pdlp_shard_check_mid(pdlp_handle h, const double* buf3, double* buf9);
 int pdlp_shard_check_decide(pdlp_handle h, const double* buf9, int force, double* buf1);
 int pdlp_shard_check_end(pdlp_handle h, const double* buf1, pdlp_check* host_out);

@@ -32,4 +32,6 @@ if rank == 0:
     for r in runs[:4]:
         ref = r.get("reference", r)
         print("golden", r["options"], ref["k"], ref["n"], ref["j"], ref["status"], ref["obj"])
+solver.close()
+dist.barrier()
 dist.destroy_process_group()

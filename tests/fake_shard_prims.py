@@ -137,8 +137,9 @@ class FakeShardPrims:
         self._rule(float(buf4[0]), float(buf4[1]))
 
     # ---- restart test ----
-    def check_begin(self, buf3):
+    def check_begin(self, buf3, have_prev):
         s = self.s
+        s.have_prev = bool(have_prev)
         self.xsum += s.w_pending * self.x
         self.ysum += s.w_pending * self.y
         es = s.eta_sum

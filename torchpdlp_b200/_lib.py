@@ -59,6 +59,7 @@ SYMBOLS = {
     "pdlp_bytes_per_iteration": (_L, [_P]),
     "pdlp_create": (_I, [C.POINTER(_P), _I, _L, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pdlp_destroy": (_I, [_P]),
+    "pdlp_set_stream": (_I, [_P, _P]),
     "pdlp_set_iterate": (_I, [_P, _P, _P]),
     "pdlp_get_iterate": (_I, [_P, _P, _P]),
     "pdlp_get_average": (_I, [_P, _P, _P]),
@@ -87,7 +88,7 @@ SYMBOLS = {
     "pdlp_shard_step": (_I, [_P, _P, _I]),
     "pdlp_shard_rule_pack": (_I, [_P, _P]),
     "pdlp_shard_rule_apply": (_I, [_P, _P]),
-    "pdlp_shard_check_begin": (_I, [_P, _P]),
+    "pdlp_shard_check_begin": (_I, [_P, _P, _I]),
     "pdlp_shard_check_mid": (_I, [_P, _P, _P]),
     "pdlp_shard_check_decide": (_I, [_P, _P, _I, _P]),
     "pdlp_shard_check_end": (_I, [_P, _P, C.POINTER(Check)]),

@@ -790,13 +790,13 @@ static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
 }
 
 template <typename T>
-static int shard_check_begin(EngineT<T>* E, double* buf3) {
+static int shard_check_begin(EngineT<T>* E, double* buf3, int have_prev) {
   pdlp_engine* B = E->base;
   cudaStream_t st = B->stream;
   const int n = (int)B->n, m = (int)B->m;
   if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
   flush_kernel<T><<<ew_blocks(std::max(n, m), B->sms), 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, n, m,
-                                                                     E->S, B->have_prev ? 1 : 0);
+                                                                     E->S, have_prev ? 1 : 0);
   CU(cudaGetLastError());
   Spmv3Op<T> f{E->Y4, (T*)buf3};
   CU(launch_stream(E->Kt, f, st));
@@ -1010,6 +1010,12 @@ extern "C" int pdlp_destroy(pdlp_handle h) {
   cudaStreamSynchronize(h->stream);
   if (h->dtype == PDLP_F64) engine_destroy<double>(h); else engine_destroy<float>(h);
   delete h;
+  return 0;
+}
+
+extern "C" int pdlp_set_stream(pdlp_handle h, void* stream) {
+  CHECK_HANDLE(h);
+  h->stream = (cudaStream_t)stream;
   return 0;
 }
 
@@ -1279,10 +1285,10 @@ extern "C" int pdlp_shard_rule_apply(pdlp_handle h, const double* buf4) {
   CU(cudaGetLastError());
   return 0;
 }
-extern "C" int pdlp_shard_check_begin(pdlp_handle h, double* buf3) {
+extern "C" int pdlp_shard_check_begin(pdlp_handle h, double* buf3, int have_previous) {
   CHECK_HANDLE(h);
   if (!buf3) return fail(PDLP_ERR_INVALID, "null argument");
-  return DISPATCH(h, shard_check_begin, buf3);
+  return DISPATCH(h, shard_check_begin, buf3, have_previous);
 }
 extern "C" int pdlp_shard_check_mid(pdlp_handle h, const double* buf3, double* buf9) {
   CHECK_HANDLE(h);

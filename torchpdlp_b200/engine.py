@@ -135,6 +135,10 @@ class Engine:
         except Exception:
             pass
 
+    def set_stream(self, stream: "torch.cuda.Stream"):
+        check(self.lib.pdlp_set_stream(self.h, stream.cuda_stream))
+        self.stream = stream
+
     def _new(self, length):
         return torch.empty(length, dtype=self.dtype, device=self.device)
 

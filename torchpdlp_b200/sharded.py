@@ -72,8 +72,8 @@ class GpuShardPrims:
     def rule_apply(self, buf4):
         check(self.lib.pdlp_shard_rule_apply(self.h, buf4.data_ptr()))
 
-    def check_begin(self, buf3):
-        check(self.lib.pdlp_shard_check_begin(self.h, buf3.data_ptr()))
+    def check_begin(self, buf3, have_prev):
+        check(self.lib.pdlp_shard_check_begin(self.h, buf3.data_ptr(), int(bool(have_prev))))
 
     def check_mid(self, buf3, buf9):
         check(self.lib.pdlp_shard_check_mid(self.h, buf3.data_ptr(), buf9.data_ptr()))
@@ -107,6 +107,18 @@ class GpuShardPrims:
     def sync(self):
         torch.cuda.synchronize(self.device)
 
+    def capture_block(self, fn):
+        """Record fn() -- kernel launches of this engine interleaved with NCCL collectives -- into one CUDA
+        graph; returns a callable that replays it on the current stream."""
+        torch.cuda.synchronize(self.device)
+        home = self.e.stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.e.set_stream(torch.cuda.current_stream(self.device))
+            fn()
+        self.e.set_stream(home)
+        return graph.replay
+
 
 class ShardedSolver:
     """Drives one rank of the row-partitioned solve.  Exposes the three calls the restart loop needs
@@ -124,6 +136,8 @@ class ShardedSolver:
         self.buf4 = prims.buffer(4)
         self.buf1 = prims.buffer(1)
         self.collectives = 0
+        self._graphs = {}
+        self._have_prev = False
         q2, c_norm = prims.local_q_sumsq()
         t = torch.tensor([q2], dtype=torch.float64, device=self.buf.device)
         self._allreduce(t)
@@ -156,17 +170,40 @@ class ShardedSolver:
         return eta, omega, sigma
 
     # -- the three calls of the restart loop --------------------------------------------------------
-    def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = False):
+    def _iterate_eager(self, n_iters, save_previous):
+        if save_previous:
+            self._have_prev = True
         for i in range(n_iters):
             self.p.kty(self.buf)
             self._allreduce(self.buf)                              # THE exchange: n + 4 doubles
             self.p.step(self.buf, save_previous and i == n_iters - 1)
 
+    def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = False):
+        """n_iters iterations.  With use_graph the whole block -- 5 kernels and one NCCL allreduce per iteration --
+        is captured once into a CUDA graph and replayed, so the host issues one launch per restart block."""
+        if not (use_graph and n_iters > 1 and hasattr(self.p, "capture_block")):
+            return self._iterate_eager(n_iters, save_previous)
+        key = (n_iters, bool(save_previous))
+        state = self._graphs.get(key)
+        if state is None:                                          # first block: eager (sets kernel attributes,
+            self._graphs[key] = "warm"                             # opens the NCCL channels), capture on the next one
+            return self._iterate_eager(n_iters, save_previous)
+        if state == "warm":
+            before = self.collectives
+            state = self.p.capture_block(lambda: self._iterate_eager(n_iters, save_previous))
+            self.collectives = before
+            self._graphs[key] = state
+        state()
+        self.collectives += n_iters
+        if save_previous:
+            self._have_prev = True
+
     def restart_check(self, force: bool = False):
         self.p.rule_pack(self.buf4)                                # step rule of the block's last iteration
         self._allreduce(self.buf4)
         self.p.rule_apply(self.buf4)
-        self.p.check_begin(self.buf3)
+        self.p.check_begin(self.buf3, self._have_prev and not force)
+        self._have_prev = False
         self._allreduce(self.buf3)                                 # K^T y of current / average / previous iterate
         self.p.check_mid(self.buf3, self.buf9)
         self._allreduce(self.buf9)                                 # row-side KKT sums
@@ -177,12 +214,20 @@ class ShardedSolver:
     def state(self):
         return self.p.state()
 
+    def close(self):
+        """Drop the captured graphs (they hold NCCL work) and the engine; call before destroy_process_group."""
+        self._graphs.clear()
+        if hasattr(self.p, "e"):
+            torch.cuda.synchronize(self.p.device)
+            self.p.e.close()
+
     def primal_objective(self):
         raise NotImplementedError("infeasibility detection is not available in the sharded engine")
 
     # -- whole solve ----------------------------------------------------------------------------------
     def solve(self, max_kkt=100_000, tol=1e-4, restart_period=40, primal_update=False, adaptive=False,
-              time_limit=3600.0, verbose=False, power_iters=100, b0=None, x_init=None, y_init_local=None):
+              time_limit=3600.0, verbose=False, power_iters=100, b0=None, x_init=None, y_init_local=None,
+              use_graph=True):
         from .primal_dual_hybrid_gradient import run_restart_loop
         t0 = time.time()
         eta, omega, sigma = self.initial_step(power_iters, b0)
@@ -193,7 +238,7 @@ class ShardedSolver:
         self.p.enable(self.q_norm, self.c_norm)
         rank0 = (not dist.is_initialized()) or dist.get_rank(self.group) == 0
         prim_obj, k, n, j, status, trace = run_restart_loop(self, max_kkt, restart_period, time_limit, 0.0,
-                                                            verbose and rank0, False, use_graph=False, t_start=t0)
+                                                            verbose and rank0, False, use_graph=use_graph, t_start=t0)
         x, y_local = self.p.get_iterate()
         return x, y_local, prim_obj, k, n, j, status, time.time() - t0, sigma
 
