@@ -27,8 +27,12 @@ import time
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import warnings
+
 import numpy as np
 import torch
+
+warnings.filterwarnings("ignore", message=".*Sparse (CSR|invariant).*")
 
 INF = float("inf")
 

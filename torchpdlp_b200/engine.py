@@ -11,8 +11,12 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
+import warnings
+
 import numpy as np
 import torch
+
+warnings.filterwarnings("ignore", message=".*Sparse (CSR|invariant).*")
 
 from . import _lib
 from ._lib import Check, Residuals, SolveOptions, SolveResult, State, check

@@ -13,6 +13,7 @@ LP is reproducible.
 """
 from __future__ import annotations
 
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -53,6 +54,7 @@ class SyntheticLP:
         """(c, K, q, m_ineq, l, u) like reference util.mps_to_standard_form
         (PDLP/util.py:269): column vectors (n,1)/(m,1); K dense / COO / CSR."""
         import torch
+        warnings.filterwarnings("ignore", message=".*Sparse (CSR|invariant).*")
         dtype = dtype or torch.float64
         col = lambda v: torch.as_tensor(v, dtype=dtype).reshape(-1, 1).to(device)
         K = self.K

@@ -11,8 +11,12 @@ from __future__ import annotations
 import time
 from collections import OrderedDict
 
+import warnings
+
 import numpy as np
 import torch
+
+warnings.filterwarnings("ignore", message=".*Sparse (CSR|invariant).*")
 
 
 class Timer:
