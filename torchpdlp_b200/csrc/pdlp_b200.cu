@@ -42,6 +42,7 @@ struct HostSell {
   std::vector<int> long_rows;
   size_t packed_bytes = 0;
   int grid = 1;
+  int max_piece_bytes = 16;
 };
 
 static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int value_bytes, int W, int KB, int sigma,
@@ -100,7 +101,9 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     pc.data_off16 = (uint32_t)(bytes / 16);
     pc.flags |= (uint32_t)kbase[p] << 8;
     const long long steps = (long long)pc.klen * pc.nslices;
-    bytes += 16 + ((pc.flags & PIECE_FIRST) ? (size_t)pc.nslices * 128 : 0) + (size_t)steps * 32 * (4 + value_bytes);
+    const size_t pb = 16 + ((pc.flags & PIECE_FIRST) ? (size_t)pc.nslices * 128 : 0) + (size_t)steps * 32 * (4 + value_bytes);
+    P.max_piece_bytes = std::max(P.max_piece_bytes, (int)pb);
+    bytes += pb;
   }
   P.packed_bytes = bytes;
   // warps: contiguous piece ranges balanced by bytes (+ a fixed per-piece cost), cut only where rows start
@@ -181,9 +184,11 @@ struct DeviceCsr {
   double* partials = nullptr;
   unsigned int* ticket = nullptr;
   int rows = 0, cols = 0, nnz = 0, grid = 0, npieces = 0, nlong = 0;
+  int stage_bytes = 0, nstages = 2, smem_bytes = 0;
   size_t packed_bytes = 0;
   SellView<T> view() const {
-    return SellView<T>{packed, pieces, warp_begin, long_rows, nlong, rowptr, colidx, vals, partials, ticket};
+    return SellView<T>{packed, pieces, warp_begin, long_rows, nlong, rowptr, colidx, vals, partials, ticket,
+                       stage_bytes, nstages};
   }
 };
 
@@ -241,14 +246,14 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         StreamCfg<T>::SMEM_BYTES);
+                                         StreamCfg<T>::MAX_SMEM_BYTES - 4096);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(A.grid);
   cfg.blockDim = dim3(StreamCfg<T>::NT);
-  cfg.dynamicSmemBytes = StreamCfg<T>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = A.smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
@@ -290,7 +295,11 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   using Cfg = StreamCfg<T>;
   HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW,
-                               E->base->sms * E->base->ctas_per_sm);
+                               E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
+  // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows
+  A.stage_bytes = (P.max_piece_bytes + 127) / 128 * 128;
+  A.nstages = std::max(2, std::min(Cfg::SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)Cfg::W * A.stage_bytes))));
+  A.smem_bytes = Cfg::W * A.nstages * A.stage_bytes + 128;
   if (P.packed_bytes / 16 >= 0xffffffffull) return fail(PDLP_ERR_INVALID, "packed matrix exceeds 64 GiB");
   A.grid = P.grid;
   A.npieces = (int)P.pieces.size();
@@ -330,13 +339,6 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   const int m = (int)B->m, n = (int)B->n, nnz = (int)B->nnz;
   cudaStream_t st = B->stream;
   // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
-  {
-    using Rep = DualOp<T, false, false>;
-    CU(cudaFuncSetAttribute(stream_kernel<Rep>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::SMEM_BYTES));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel<Rep>, StreamCfg<T>::NT, StreamCfg<T>::SMEM_BYTES));
-    B->ctas_per_sm = std::max(1, occ);
-  }
   int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals);
   if (rc) return rc;
   rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals);
@@ -438,7 +440,7 @@ static cudaError_t enqueue_iterations(EngineT<T>* E, int n_iters, int save_prev,
 template <class Op>
 static cudaError_t prep_kernel() {
   return cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              StreamCfg<typename Op::value_type>::SMEM_BYTES);
+                              StreamCfg<typename Op::value_type>::MAX_SMEM_BYTES - 4096);
 }
 
 template <typename T>

@@ -25,9 +25,18 @@ namespace pdlp {
 #ifndef PDLP_W
 #define PDLP_W 12         // warps per CTA
 #endif
-#ifndef PDLP_S
-#define PDLP_S 2          // ring stages per warp
+#ifndef PDLP_SMAX
+#define PDLP_SMAX 8       // upper bound on ring stages per warp (the plan picks S <= SMAX from the shared-memory budget)
 #endif
+#ifndef PDLP_CTAS
+#define PDLP_CTAS 1       // CTAs per SM the shared-memory budget is split over
+#endif
+#ifndef PDLP_OVERSUB
+#define PDLP_OVERSUB 1    // grid = resident CTAs x OVERSUB.  Measured on config 2: 1 -> 66 us, 2 -> 79 us, 4 -> 87 us per
+#endif                    // iteration: extra waves cost more in pipeline ramp-up than they gain in balance
+#ifndef PDLP_SMEM_BUDGET
+#define PDLP_SMEM_BUDGET (128 * 1024)   // shared memory per SM given to the rings.  The rest of the 228 KB stays L1, which
+#endif                                  // holds the gathers in flight: 64-128 KB -> 66 us, 160 KB -> 68 us, 200 KB -> 108 us
 #ifndef PDLP_KB
 #define PDLP_KB 8         // steps (elements per lane) per piece
 #endif
@@ -69,20 +78,21 @@ struct SellView {
   const T* vals;
   double* block_partials;        // gridDim.x * MAX_RED
   unsigned int* ticket;
+  int stage_bytes;               // ring stage size: the largest piece of this matrix, rounded up to 128
+  int nstages;                   // ring stages per warp (2 .. SMAX)
 };
 
 template <typename T>
 struct StreamCfg {
   static constexpr int W = PDLP_W;
   static constexpr int NT = W * 32;
-  static constexpr int S = PDLP_S;
+  static constexpr int SMAX = PDLP_SMAX;
   static constexpr int KB = PDLP_KB;
   static constexpr int U = PDLP_U;
   static constexpr int MINB = PDLP_MINB;
   static constexpr int MAXSL = 16;                 // slices per piece (short rows)
-  static constexpr int STAGE_BYTES = 16 + MAXSL * 128 + KB * 32 * (4 + (int)sizeof(T));
-  static constexpr int RING_BYTES = S * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = W * RING_BYTES + 128;
+  static constexpr int MAX_STAGE_BYTES = 16 + MAXSL * 128 + KB * 32 * (4 + (int)sizeof(T));
+  static constexpr int MAX_SMEM_BYTES = 227 * 1024;
 };
 
 // developer experiments (never defined in product builds): isolate pipeline components when timing
@@ -158,7 +168,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   constexpr int U = (Cfg::U / Op::UDIV) > 0 ? (Cfg::U / Op::UDIV) : 1;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[Cfg::W][Cfg::S];
+  __shared__ uint64_t full_bar[Cfg::W][Cfg::SMAX];
   __shared__ double s_red[Cfg::W][NR > NV ? NR : NV];
   __shared__ int s_last;
 
@@ -166,8 +176,10 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  const int S = A.nstages;
+  const int stage_bytes = A.stage_bytes;
   if (lane == 0) {
-    for (int s = 0; s < Cfg::S; ++s) mbar_init(&full_bar[warp][s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&full_bar[warp][s], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -180,7 +192,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   const int gw = blockIdx.x * Cfg::W + warp;
   const int pb = A.warp_piece_begin[gw];
   const int pe = A.warp_piece_begin[gw + 1];
-  unsigned char* ring = smem + (size_t)warp * Cfg::RING_BYTES;
+  unsigned char* ring = smem + (size_t)warp * S * stage_bytes;
 
   auto piece_bytes = [](const Piece& d) -> uint32_t {
     return 16u + ((d.flags & PIECE_FIRST) ? (uint32_t)d.nslices * 128u : 0u) +
@@ -188,11 +200,11 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   };
   // prologue: fill the ring (before the long rows so the copies fly meanwhile)
   if (lane == 0) {
-    for (int s = 0; s < Cfg::S && pb + s < pe; ++s) {
+    for (int s = 0; s < S && pb + s < pe; ++s) {
       const Piece d = A.pieces[pb + s];
       const uint32_t bytes = piece_bytes(d);
       mbar_arrive_expect_tx(&full_bar[warp][s], bytes);
-      tma_load_1d(ring + (size_t)s * Cfg::STAGE_BYTES, A.packed + (size_t)d.data_off16 * 16u, bytes, &full_bar[warp][s]);
+      tma_load_1d(ring + (size_t)s * stage_bytes, A.packed + (size_t)d.data_off16 * 16u, bytes, &full_bar[warp][s]);
     }
   }
 
@@ -202,7 +214,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!op.begin()) {
     // drain the copies already in flight before the CTA may retire
-    for (int s = 0; s < Cfg::S && pb + s < pe; ++s) mbar_wait(&full_bar[warp][s], 0);
+    for (int s = 0; s < S && pb + s < pe; ++s) mbar_wait(&full_bar[warp][s], 0);
     return;
   }
 
@@ -249,11 +261,11 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
     typename Op::Ctx ctx;
     int row = -1;
     typename Op::Gather g_cur[U], g_nxt[U];
-    auto stage_of = [&](int p) { return ring + (size_t)((p - pb) % Cfg::S) * Cfg::STAGE_BYTES; };
+    auto stage_of = [&](int p) { return ring + (size_t)((p - pb) % S) * stage_bytes; };
     // first batch of a piece: slice 0, steps [0, min(U, klen))
     auto issue_first = [&](int p, typename Op::Gather (&g)[U]) {
       const int it = p - pb;
-      mbar_wait(&full_bar[warp][it % Cfg::S], (it / Cfg::S) & 1);
+      mbar_wait(&full_bar[warp][it % S], (it / S) & 1);
       const unsigned char* st = stage_of(p);
       const Piece d = *reinterpret_cast<const Piece*>(st);
       const int* cols = reinterpret_cast<const int*>(st + 16) + ((d.flags & PIECE_FIRST) ? (int)d.nslices * 32 : 0);
@@ -265,9 +277,9 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
     if (pb < pe) issue_first(pb, g_cur);
     for (int p = pb; p < pe; ++p) {
       Piece d_refill = Piece{0, 0, 0, 0, 0};
-      const bool refill = (p + Cfg::S < pe);
-      if (refill && lane == 0) d_refill = A.pieces[p + Cfg::S];     // used after this piece: latency hidden
-      const int s = (p - pb) % Cfg::S;
+      const bool refill = (p + S < pe);
+      if (refill && lane == 0) d_refill = A.pieces[p + S];          // used after this piece: latency hidden
+      const int s = (p - pb) % S;
       const unsigned char* st = stage_of(p);
       const Piece d = *reinterpret_cast<const Piece*>(st);          // stage already waited for by issue_first
       const int klen = d.klen;
@@ -323,7 +335,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
       if (refill && lane == 0) {
         const uint32_t bytes = piece_bytes(d_refill);
         mbar_arrive_expect_tx(&full_bar[warp][s], bytes);
-        tma_load_1d(ring + (size_t)s * Cfg::STAGE_BYTES, A.packed + (size_t)d_refill.data_off16 * 16u, bytes,
+        tma_load_1d(ring + (size_t)s * stage_bytes, A.packed + (size_t)d_refill.data_off16 * 16u, bytes,
                     &full_bar[warp][s]);
       }
 #pragma unroll
