@@ -401,7 +401,7 @@ def run_sharded(args, world, rank, local, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     args = ap.parse_args()

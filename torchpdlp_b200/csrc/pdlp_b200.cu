@@ -223,6 +223,9 @@ struct EngineT {
   // cached graphs for pdlp_iterate
   struct GraphEntry { int n_iters; int save_prev; int infeas; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
+  cudaGraphExec_t check_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [force][have_prev]
+  bool check_warm[2][2] = {{false, false}, {false, false}};
+  Scalars* h_scalars = nullptr;          // pinned read-back buffer
   std::vector<void*> allocs;
 };
 
@@ -352,7 +355,8 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   CU(cudaMemsetAsync(E->kty_old, 0, sizeof(T) * n, st));
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
   ALLOC(E->S, 1);
-  E->ew_grid = B->sms * 4;
+  E->ew_grid = B->sms * 2;
+  CU(cudaMallocHost((void**)&E->h_scalars, sizeof(Scalars)));
   ALLOC(E->ew_partials, 2 * E->ew_grid);
   ALLOC(E->kkt_partials, 16 * E->ew_grid);
   ALLOC(E->ew_ticket, 1);
@@ -382,6 +386,10 @@ static void engine_destroy(pdlp_engine* B) {
   EngineT<T>* E = (EngineT<T>*)B->impl;
   if (!E) return;
   for (auto& g : E->graphs) cudaGraphExecDestroy(g.exec);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
+  if (E->h_scalars) cudaFreeHost(E->h_scalars);
   for (void* p : E->allocs) cudaFreeAsync(p, B->stream);
   cudaStreamSynchronize(B->stream);
   delete E;
@@ -547,11 +555,9 @@ static void fill_check(pdlp_check* out, const Scalars& h) {
 }
 
 template <typename T>
-static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
+static int enqueue_check(EngineT<T>* E, int force, int have_prev, cudaStream_t st) {
   pdlp_engine* B = E->base;
-  cudaStream_t st = B->stream;
   const int n = (int)B->n, m = (int)B->m;
-  const int have_prev = (B->have_prev && !force) ? 1 : 0;
   flush_kernel<T><<<ew_blocks(std::max(n, m), B->sms), 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, n, m,
                                                                      E->S, have_prev);
   CU(cudaGetLastError());
@@ -562,11 +568,47 @@ static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
                                                       n, m, E->S, E->ew_partials, E->ew_ticket);
   post_restart_kernel<<<1, 1, 0, st>>>(E->S, B->scaled ? 1 : 0);
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(E->h_scalars, E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// the restart test is one cached CUDA graph (7 kernels + the read-back copy) per (force, have_prev) pair
+template <typename T>
+static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int have_prev = (B->have_prev && !force) ? 1 : 0;
+  const int f = force ? 1 : 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  CU(cudaStreamIsCapturing(st, &cs));
+  if (cs != cudaStreamCaptureStatusNone) return fail(PDLP_ERR_STATE, "pdlp_restart_check synchronises: not capturable");
+  if (!E->check_graph[f][have_prev]) {
+    // first use: run eagerly once (sets kernel attributes), capture for the following calls
+    if (E->check_warm[f][have_prev]) {
+      cudaStream_t cap;
+      CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_check<T>(E, force, have_prev, cap);
+      cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
+      if (rc || e2 != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        return rc ? rc : fail(PDLP_ERR_CUDA, std::string("check capture failed: ") + cudaGetErrorString(e2));
+      }
+      CU(cudaGraphInstantiate(&E->check_graph[f][have_prev], graph, 0));
+      cudaGraphDestroy(graph);
+      cudaStreamDestroy(cap);
+    } else {
+      E->check_warm[f][have_prev] = true;
+      int rc = enqueue_check<T>(E, force, have_prev, st);
+      if (rc) return rc;
+    }
+  }
+  if (E->check_graph[f][have_prev]) CU(cudaGraphLaunch(E->check_graph[f][have_prev], st));
   B->have_prev = false;
-  Scalars h;
-  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (out) fill_check(out, h);
+  if (out) fill_check(out, *E->h_scalars);
   return 0;
 }
 

@@ -880,13 +880,20 @@ __global__ void apply_restart_kernel(Pair<T>* xp, T* y, T* xsum, T* ysum, const 
     s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && warp == 0) {
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (int bl = 0; bl < (int)gridDim.x; ++bl) { a += __ldcg(&partials[2 * bl]); b += __ldcg(&partials[2 * bl + 1]); }
-    S->restart_dx2 = a;
-    S->restart_dy2 = b;
-    *ticket = 0u;
+    for (int bl = lane; bl < (int)gridDim.x; bl += 32) { a += __ldcg(&partials[2 * bl]); b += __ldcg(&partials[2 * bl + 1]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      S->restart_dx2 = a;
+      S->restart_dy2 = b;
+      *ticket = 0u;
+    }
   }
 }
 
