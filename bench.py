@@ -226,13 +226,16 @@ def run_engine(args):
     barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
+    solve_device_ms = []
     for _ in range(n_solves):
         _cache.clear()
         torch.manual_seed(0)
-        x, obj, k, n, j, status, secs = pdlp_algorithm(Kh, m_ineq, host[3], host[4], host[5], host[6], dev, verbose=False,
-                                                       adaptive=True, primal_update=True)
+        x, obj, k, n, j, status, secs, info = pdlp_algorithm(Kh, m_ineq, host[3], host[4], host[5], host[6], dev,
+                                                             verbose=False, adaptive=True, primal_update=True,
+                                                             return_info=True)
         x_host = x.cpu()
         e2e_iters += k
+        solve_device_ms.append(info.get("device_ms"))
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -267,6 +270,9 @@ def run_engine(args):
                        "sigma_max": sigma, "bytes_per_iteration": b_iter},
             "us_per_iteration": 1e3 * ms / iters,
             "iteration_roofline_frac": b_iter / (ms * 1e-3 / iters) / 1e9 / peak,
+            "time_to_tolerance": {"rel_kkt": 1e-4, "iterations": e2e_iters // n_solves, "status": status,
+                                  "device_ms": min(v for v in solve_device_ms if v) if any(solve_device_ms) else None,
+                                  "wall_s_from_host_tensors": e2e_s / n_solves},
             "gpu_launches": KERNELS_PER_STEP * args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -138,6 +138,7 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
     engine.set_counters(0, 0)
     engine.set_step(eta, omega, 1.0, adaptive)
     engine.set_options(tol, primal_update, infeasibility_detect, infeas_tol)
+    device_ms = None
     if verbose:
         prim_obj, k, n, j, status, trace = run_restart_loop(engine, max_kkt, restart_period, time_limit, time_used,
                                                             verbose, scaled, use_graph, t_start,
@@ -145,11 +146,12 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
     else:
         out = engine.solve(max_kkt, restart_period, time_limit, time_used + (time.time() - t_start), use_graph)
         prim_obj, k, n, j, status, trace = out.prim_obj, out.k, out.n, out.j, out.status, out.trace
+        device_ms = out.device_ms
     x, y = engine.get_iterate()
     torch.cuda.synchronize(engine.device)
     total = time.time() - t_start + time_used
     if return_info:
-        info = {"y": y.reshape(-1, 1), "trace": trace, "sigma_max": sigma, "engine": engine,
+        info = {"y": y.reshape(-1, 1), "trace": trace, "sigma_max": sigma, "engine": engine, "device_ms": device_ms,
                 "bytes_per_iteration": engine.bytes_per_iteration}
         return x.reshape(-1, 1), prim_obj, k, n, j, status, total, info
     return x.reshape(-1, 1), prim_obj, k, n, j, status, total
