@@ -146,7 +146,11 @@ int pdlp_set_counters(pdlp_handle h, int64_t k, int32_t t);
  * adaptive_one_step_pdhg step.py:43-115, plus the averaging update :104-112),
  * two kernels per iteration, scalars stay on the device.  With
  * save_previous != 0 the iterate before the LAST step is kept for the restart
- * test (:77-78,:126).  use_graph != 0 replays a cached CUDA graph.  Async.    */
+ * test (:77-78,:126).  use_graph: 0 = one launch per kernel; 1 = replay a cached
+ * CUDA graph of the block; 2 = ONE persistent cooperative kernel for the whole block
+ * (grid barriers between the passes, step rule evaluated by every CTA; not with
+ * infeasibility detection, which falls back to 1).  All three give bitwise the same
+ * iterates.  Async.                                                             */
 int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int use_graph);
 
 /* Measurement aid for bench.py: run n_iters iterations WITHOUT a graph, bracketing every

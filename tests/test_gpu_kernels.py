@@ -171,6 +171,28 @@ def test_step_functions_reference_pins(cfg1, fp64_default):
     assert j == 1
 
 
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_loop_modes_bitwise_identical(which, cfg1):
+    """Eager launches, the CUDA graph and the persistent cooperative kernel give bit-identical iterates and scalars."""
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    outs = []
+    for mode in (0, 1, 2):
+        eng = make_engine(lp)
+        eng.set_iterate(None, None)
+        eng.set_step(0.1, 0.5, 1.0, adaptive=True)
+        eng.set_options(1e-4, True, False, 1e-4)
+        for _ in range(3):
+            eng.iterate(40, save_previous=True, use_graph=mode)
+            chk = eng.restart_check(False)
+        eng.iterate(7, save_previous=False, use_graph=mode)
+        x, y = eng.get_iterate()
+        st = eng.state()
+        outs.append((x.cpu(), y.cpu(), st.eta, st.eta_sum, st.k, st.t, chk.kkt_current, chk.kkt_previous))
+        eng.close()
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and o[2:] == outs[0][2:]
+
+
 def test_bitwise_reproducible(cfg1):
     """No atomics on data: two runs of 80 iterations give bit-identical iterates."""
     outs = []

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/pdlp_b200.h"
+#include "pdlp_block.cuh"
 #include "pdlp_ops.cuh"
 
 using namespace pdlp;
@@ -188,7 +189,7 @@ struct DeviceCsr {
   size_t packed_bytes = 0;
   SellView<T> view() const {
     return SellView<T>{packed, pieces, warp_begin, long_rows, nlong, rowptr, colidx, vals, partials, ticket,
-                       stage_bytes, nstages};
+                       stage_bytes, nstages, grid};
   }
 };
 
@@ -218,6 +219,8 @@ struct EngineT {
   Scalars* S = nullptr;
   double* ew_partials = nullptr;
   double* kkt_partials = nullptr;   // sharded KKT column sums: ew_grid x 16
+  double *blk_partP = nullptr, *blk_partD = nullptr;   // persistent block kernel: per-CTA partial norms (double-buffered)
+  unsigned int* blk_bar = nullptr;
   unsigned int* ew_ticket = nullptr;
   int ew_grid = 0;
   // cached graphs for pdlp_iterate
@@ -359,6 +362,9 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   CU(cudaMallocHost((void**)&E->h_scalars, sizeof(Scalars)));
   ALLOC(E->ew_partials, 2 * E->ew_grid);
   ALLOC(E->kkt_partials, 16 * E->ew_grid);
+  ALLOC(E->blk_partP, 2 * B->sms * 4);
+  ALLOC(E->blk_partD, 4 * B->sms * 4);
+  ALLOC(E->blk_bar, 4);
   ALLOC(E->ew_ticket, 1);
   CU(cudaMemsetAsync(E->ew_ticket, 0, sizeof(unsigned int), st));
   CU(cudaMemcpyAsync(E->c, c, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
@@ -457,10 +463,30 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   cudaStream_t st = B->stream;
   if (n_iters <= 0) return 0;
   if (save_prev) B->have_prev = true;
+  if (use_graph == 2 && !B->infeas) {
+    // one persistent cooperative kernel for the whole block
+    const int grid = std::max(E->K.grid, E->Kt.grid);
+    const int stages = std::min(E->K.nstages, E->Kt.nstages);
+    const int stage_bytes = std::max(E->K.stage_bytes, E->Kt.stage_bytes);
+    const int smem = StreamCfg<T>::W * stages * stage_bytes + 128;
+    static bool attr = false;
+    if (!attr) {
+      CU(cudaFuncSetAttribute(block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
+      attr = true;
+    }
+    CU(cudaMemsetAsync(E->blk_bar, 0, sizeof(unsigned int), st));
+    SellView<T> vKt = E->Kt.view(), vK = E->K.view();
+    BlockArgs<T> a{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->q, E->ysum, E->Y4, E->kty_old, E->S,
+                   E->blk_partP, E->blk_partD, E->blk_bar, n_iters, save_prev ? 1 : 0, stages, stage_bytes};
+    void* args[] = {(void*)&vKt, (void*)&vK, (void*)&a};
+    CU(cudaLaunchCooperativeKernel((const void*)block_kernel<T>, dim3(grid), dim3(StreamCfg<T>::NT), args, (size_t)smem, st));
+    return 0;
+  }
   if (!use_graph || n_iters < 2) {
     CU(enqueue_iterations<T>(E, n_iters, save_prev, st));
     return 0;
   }
+  // (mode 2 with infeasibility detection lands here: CUDA graph)
   const int inf = B->infeas ? 1 : 0;
   for (auto& g : E->graphs)
     if (g.n_iters == n_iters && g.save_prev == (save_prev ? 1 : 0) && g.infeas == inf) {

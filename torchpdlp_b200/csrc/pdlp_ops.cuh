@@ -122,6 +122,7 @@ struct SpmvOp {
   static constexpr int NV = 1;
   static constexpr int NRED = SUMSQ ? 1 : 0;
   static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
   const T* in;
   T* out;
   Scalars* S;
@@ -149,6 +150,7 @@ struct PrimalOp {
   static constexpr int NV = 1;
   static constexpr int NRED = INFEAS ? 3 : 1;
   static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
   const T* y;
   const T* c;
   const T* l;
@@ -159,6 +161,7 @@ struct PrimalOp {
   Scalars* S;
   T* kty_old;        // INFEAS: K^T y of the iterate the step started from
   T tau, wpend, itol;
+  bool do_save = true;   // runtime gate of SAVE_PREV (the persistent kernel saves only on its last iteration)
   __device__ bool begin() {
     if (S->stop) return false;
     tau = (T)(S->eta / S->omega);
@@ -175,7 +178,7 @@ struct PrimalOp {
     const T dx = xn - k.xo;
     xp[j] = Pair<T>{xn, dx};
     xsum[j] = k.xs + wpend * k.xo;
-    if (SAVE_PREV) X4[j].v[IT_PREV] = k.xo;
+    if (SAVE_PREV && do_save) X4[j].v[IT_PREV] = k.xo;
     red[0] += (double)dx * (double)dx;
     if (INFEAS) {
       kty_old[j] = acc[0];
@@ -206,6 +209,7 @@ struct DualOp {
   static constexpr int NV = 2;
   static constexpr int NRED = INFEAS ? 6 : 2;
   static constexpr int UDIV = 1;
+  static constexpr int PIPE = 0;   // 16-byte gathers: a second batch buffer costs 32 registers for ~2 %
   const Pair<T>* xp;
   const T* q;
   T* y;
@@ -214,6 +218,7 @@ struct DualOp {
   Scalars* S;
   T sigma, theta, wpend, itol;
   int m_ineq;
+  bool do_save = true;
   __device__ bool begin() {
     if (S->stop) return false;
     sigma = (T)(S->eta * S->omega);
@@ -235,7 +240,7 @@ struct DualOp {
     const T dy = yn - k.yo;
     y[i] = yn;
     ysum[i] = k.ys + wpend * k.yo;
-    if (SAVE_PREV) Y4[i].v[IT_PREV] = k.yo;
+    if (SAVE_PREV && do_save) Y4[i].v[IT_PREV] = k.yo;
     red[0] += (double)dy * (double)dy;
     red[1] += (double)dy * (double)acc[1];
     if (INFEAS) {
@@ -288,6 +293,7 @@ struct InfeasColsOp {
   static constexpr int NV = 1;
   static constexpr int NRED = 3;
   static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
   const T* y;
   const T* c;
   const T* l;
@@ -344,6 +350,7 @@ struct KktColsOp {
   static constexpr int NV = 3;
   static constexpr int NRED = 15;   // per iterate: dr2, cTx, lpos, uneg, dr2u
   static constexpr int UDIV = 2;
+  static constexpr int PIPE = 0;
   const Quad<T>* Y4;
   const Quad<T>* X4;
   const T* c;
@@ -403,6 +410,7 @@ struct KktRowsOp {
   static constexpr int NV = 3;
   static constexpr int NRED = 9;    // per iterate: pr2, qTy, pr2u
   static constexpr int UDIV = 2;
+  static constexpr int PIPE = 0;
   const Quad<T>* X4;
   const Quad<T>* Y4;
   const T* q;
@@ -450,6 +458,7 @@ struct BatchOp {
   static constexpr int NV = 8;
   static constexpr int NRED = 0;
   static constexpr int UDIV = 4;
+  static constexpr int PIPE = 0;
   const Oct<T>* in;      // gathered operand
   Oct<T>* out;           // MODE 0: Y8; MODE 1: X8 (updated in place); MODE 2: Y8 (in place)
   Oct<T>* aux;           // MODE 1: XB8
@@ -509,6 +518,7 @@ struct BatchGapOp {
   static constexpr int NV = 8;
   static constexpr int NRED = 24;
   static constexpr int UDIV = 4;
+  static constexpr int PIPE = 0;
   const Oct<T>* Y8;
   const Oct<T>* X8;
   const T* c;
@@ -558,6 +568,7 @@ struct Spmv3Op {
   static constexpr int NV = 3;
   static constexpr int NRED = 0;
   static constexpr int UDIV = 2;
+  static constexpr int PIPE = 0;
   const Quad<T>* Y4;
   T* out3;
   __device__ bool begin() { return true; }

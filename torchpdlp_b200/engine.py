@@ -8,6 +8,7 @@ CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -29,6 +30,21 @@ STATUS_STRINGS = {
     4: "DUAL_INFEASIBLE",                          # enhancements.py:141
 }
 RESTART_KINDS = {0: None, 1: "Sufficient", 2: "Necessary", 3: "Artificial", 4: "Limit"}
+
+# how a block of iterations is issued: 0 = one launch per kernel, 1 = CUDA graph of the block's kernels,
+# 2 = ONE persistent cooperative kernel per block (grid barriers instead of kernel boundaries)
+LOOP_EAGER, LOOP_GRAPH, LOOP_PERSISTENT = 0, 1, 2
+# Measured on B200 (round 1): graph + programmatic dependent launch 66 us/iteration on config 2 and 16 us on
+# config 1; the persistent kernel 72 us and 16 us (two grid barriers + a redundant grid reduction per iteration
+# cost as much as the two dependent launches they replace), so the graph is the default.
+DEFAULT_LOOP_MODE = int(os.environ.get("PDLP_LOOP_MODE", LOOP_GRAPH))
+
+
+def loop_mode(use_graph) -> int:
+    """bool / int -> loop mode: True means "the fastest loop" (DEFAULT_LOOP_MODE), False eager."""
+    if use_graph is True:
+        return DEFAULT_LOOP_MODE
+    return int(use_graph)
 
 
 def _require_cuda(device) -> torch.device:
@@ -185,8 +201,8 @@ class Engine:
         return s
 
     # -- hot loop -----------------------------------------------------------
-    def iterate(self, n_iters: int, save_previous: bool = False, use_graph: bool = True):
-        check(self.lib.pdlp_iterate(self.h, int(n_iters), int(bool(save_previous)), int(bool(use_graph))))
+    def iterate(self, n_iters: int, save_previous: bool = False, use_graph=True):
+        check(self.lib.pdlp_iterate(self.h, int(n_iters), int(bool(save_previous)), loop_mode(use_graph)))
 
     def time_kernels(self, n_iters: int):
         """Average device milliseconds per launch of the (primal, dual) iteration kernels."""
@@ -256,7 +272,7 @@ class Engine:
     # -- whole solve ----------------------------------------------------------
     def solve(self, max_kkt=100_000, restart_period=40, time_limit=3600.0, time_used=0.0, use_graph=True,
               max_trace=4096) -> SolveOutput:
-        opts = SolveOptions(int(max_kkt), int(restart_period), int(bool(use_graph)), float(time_limit),
+        opts = SolveOptions(int(max_kkt), int(restart_period), loop_mode(use_graph), float(time_limit),
                             float(time_used), int(max_trace), 0)
         res = SolveResult()
         trace = (Check * max(1, max_trace))()
