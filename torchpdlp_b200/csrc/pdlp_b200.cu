@@ -246,8 +246,31 @@ static int dev_alloc(EngineT<T>* E, void** p, size_t bytes) {
     if (rc_) return rc_;                                                                   \
   } while (0)
 
+// L2 residency of the gathered operand.  The matrix stream carries an evict-first hint (stream_spmv.cuh), which
+// is what helps (config 4: 1142 -> 987 us per iteration, config 2: 65.4 -> 63.7 us).  A per-launch access-policy
+// window marking the operand "persisting" on top of it was measured too and made things WORSE (config 4:
+// 993 -> 1195 us), so it is compiled in only with -DPDLP_L2_WINDOW.
+static size_t g_l2_window_max = 0;
+static void init_l2_persistence() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+#ifdef PDLP_L2_WINDOW
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+  if (prop.persistingL2CacheMaxSize <= 0) return;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  g_l2_window_max = std::min((size_t)prop.accessPolicyMaxWindowSize, (size_t)prop.persistingL2CacheMaxSize);
+#endif
+}
+
 template <class Op>
-static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st) {
+static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st,
+                                 const void* gathered = nullptr, size_t gathered_bytes = 0) {
   using T = typename Op::value_type;
   static bool attr_set = false;
   if (!attr_set) {
@@ -261,11 +284,20 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
   cfg.blockDim = dim3(StreamCfg<T>::NT);
   cfg.dynamicSmemBytes = A.smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (gathered && gathered_bytes && g_l2_window_max) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(gathered);
+    attr[1].val.accessPolicyWindow.num_bytes = std::min(gathered_bytes, g_l2_window_max);
+    attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, stream_kernel<Op>, A.view(), op);
 }
 
@@ -426,10 +458,10 @@ static int refresh_norms(EngineT<T>* E) {
 template <typename T, bool SP, bool INF>
 static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
   PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
-  cudaError_t e = launch_stream(E->Kt, p, st);
+  cudaError_t e = launch_stream(E->Kt, p, st, E->y, sizeof(T) * (size_t)E->base->m);
   if (e != cudaSuccess) return e;
   DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-  e = launch_stream(E->K, d, st);
+  e = launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
   if (e != cudaSuccess) return e;
   if (INF) {
     InfeasColsOp<T> f{E->y, E->c, E->l, E->u, E->kty_old, E->lam_prev, E->S};
@@ -1054,6 +1086,7 @@ extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, in
   B->dtype = dtype; B->device = dev; B->stream = (cudaStream_t)stream;
   B->m = m; B->n = n; B->m_ineq = m_ineq; B->nnz = nnz;
   B->sms = prop.multiProcessorCount;
+  init_l2_persistence();
   {
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, dev));
