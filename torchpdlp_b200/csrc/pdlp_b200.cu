@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -56,7 +57,29 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     if (len(r) > long_row) P.long_rows.push_back(r);
     else order.push_back(r);
   }
-  // sort by length (descending, stable) inside windows of sigma rows: neighbours in a slice get equal lengths
+  // Sort by length (descending, stable) inside windows of sigma rows: neighbours in a slice get equal lengths.
+  // sigma is adaptive: the smallest window (starting from the requested one) whose padded size stays within 5 % of
+  // the nonzeros -- heavy-tailed row lengths need a wide window (config 4: 1.74x padding at 1024 rows, 1.05x at
+  // 16384), uniform ones keep the narrow window and with it the locality of the row epilogue.
+  {
+    std::vector<int> tmp;
+    long long nnz_short = 0;
+    for (int r : order) nnz_short += len(r);
+    int best = sigma;
+    for (int cand = sigma; cand <= (1 << 18); cand *= 4) {
+      best = cand;
+      long long padded = 0;
+      for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)cand) {
+        const size_t w1 = std::min(order.size(), w0 + (size_t)cand);
+        tmp.clear();
+        for (size_t i = w0; i < w1; ++i) tmp.push_back(len(order[i]));
+        std::sort(tmp.begin(), tmp.end(), std::greater<int>());
+        for (size_t i = 0; i < tmp.size(); i += 32) padded += 32LL * tmp[i];
+      }
+      if (padded <= nnz_short + nnz_short / 20 || (size_t)cand >= order.size()) break;
+    }
+    sigma = best;
+  }
   for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {
     const size_t w1 = std::min(order.size(), w0 + (size_t)sigma);
     std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return len(a) > len(b); });

@@ -76,6 +76,29 @@ __device__ __forceinline__ Pair<float> ldg(const Pair<float>* p) {
 
 template <typename T> __device__ __forceinline__ T clampv(T v, T lo, T hi) { return fmin(fmax(v, lo), hi); }
 
+#ifdef PDLP_GATHER_EVICT_LAST
+// gathers of the dense operand with an L2 evict-last hint (developer experiment)
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ldg_keep(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(l2_evict_last_policy()));
+  return v;
+}
+__device__ __forceinline__ Pair<double> ldg_keep(const Pair<double>* p) {
+  Pair<double> v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.a), "=d"(v.b) : "l"(p), "l"(l2_evict_last_policy()));
+  return v;
+}
+__device__ __forceinline__ float ldg_keep(const float* p) { return __ldg(p); }
+__device__ __forceinline__ Pair<float> ldg_keep(const Pair<float>* p) { return ldg(p); }
+#else
+template <typename P> __device__ __forceinline__ auto ldg_keep(const P* p) { return ldg(p); }
+#endif
+
 // The step-size rule: step.py:96-115 (adaptive) / :40 (fixed).  Increments k (pdlp :76 counts the iteration
 // before the rule reads it) and returns the averaging weight of the new iterate and the next step size.
 __device__ inline void step_rule(Scalars& s, double dx2, double dy2, double inter, double& w, double& next) {
@@ -169,7 +192,7 @@ struct PrimalOp {
     itol = (T)S->infeas_tol;
     return true;
   }
-  __device__ T gather(int col) const { return ldg(y + col); }
+  __device__ T gather(int col) const { return ldg_keep(y + col); }
   __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
   __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], xp[j].a, xsum[j]}; }
   __device__ void row_finish(int j, const Ctx& k, const T (&acc)[1], double (&red)[NRED]) {
@@ -228,7 +251,7 @@ struct DualOp {
     m_ineq = S->m_ineq;
     return true;
   }
-  __device__ Pair<T> gather(int col) const { return ldg(xp + col); }
+  __device__ Pair<T> gather(int col) const { return ldg_keep(xp + col); }
   __device__ void mac(T (&acc)[2], T a, const Pair<T>& p) const {
     acc[0] += a * (p.a + theta * p.b);
     acc[1] += a * p.b;

@@ -230,7 +230,21 @@ __device__ __forceinline__ void stream_phase(const SellView<typename Op::value_t
       T acc[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[v] = T(0);
-      for (int i = b + tid; i < e; i += Cfg::NT) op.mac(acc, A.vals[i], op.gather(PDLP_COL(A.colidx[i])));
+      for (int i = b + tid; i < e; i += U * Cfg::NT) {       // U independent gathers per thread and batch
+        typename Op::Gather g[U];
+        T a[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int idx = i + j * Cfg::NT;
+          if (idx < e) {
+            g[j] = op.gather(PDLP_COL(A.colidx[idx]));
+            a[j] = A.vals[idx];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (i + j * Cfg::NT < e) op.mac(acc, a[j], g[j]);
+      }
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
 #pragma unroll
