@@ -38,6 +38,8 @@ for graph in (False, True):
     ms = e0.elapsed_time(e1) / 400
     print(f"graph={graph}: {ms*1e3:.2f} us/iter  {1e3/ms:.0f} it/s  {eng.bytes_per_iteration/ms/1e6:.0f} GB/s "
           f"= {eng.bytes_per_iteration/ms/1e6/6542.1*100:.1f}% of 6542 GB/s")
+a, b = eng.time_kernels(40)
+print(f"kernels: primal {a*1e3:.1f} us  dual {b*1e3:.1f} us")
 if os.environ.get("PDLP_TIMING_ONLY"):
     sys.exit(0)
 t0 = time.time(); chk = eng.restart_check(False); torch.cuda.synchronize(); print(f"restart check {1e3*(time.time()-t0):.3f} ms kind={chk.kind}")
