@@ -114,6 +114,23 @@ def test_cfg2_full_size_against_oracle(idx):
 
 
 @pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_sharded_peer_exchange_single_rank(adaptive, pw, cfg1):
+    """The peer-memory exchange kernels (flags, segment reduce/push, deferred rule) with world size 1: the same
+    k / n / j / objective as the host-allreduce path, which the next test pins to the executed reference."""
+    from torchpdlp_b200.sharded import build_rank_engine
+    torch.set_default_dtype(torch.float64)
+    outs = []
+    for exchange in ("nccl", "p2p"):
+        solver = build_rank_engine(cfg1.K, cfg1.m_ineq, cfg1.c, cfg1.q, cfg1.l, cfg1.u, exchange=exchange)
+        torch.manual_seed(0)
+        x, y, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=pw)
+        outs.append((x.cpu(), y.cpu(), obj, k, n, j, status))
+        solver.close()
+    assert outs[0][2:] == outs[1][2:]
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
 def test_sharded_entry_points_single_rank(adaptive, pw, cfg1):
     """The pdlp_shard_* kernels (partial SpMV -> [allreduce] -> element-wise epilogues, deferred step
     rule) with world size 1 reproduce the fused single-GPU engine and the executed reference."""

@@ -226,7 +226,15 @@ struct pdlp_engine {
   bool have_prev = false;
   bool infeas = false;    // host mirror of Scalars::infeas_detect
   void* impl = nullptr;   // EngineT<T>*
+  // peer-memory exchange of the row-partitioned engine (pdlp_shard_exchange_*)
+  unsigned char* xchg_block = nullptr;          // this rank's part | tot | flags block (cudaMalloc, IPC-exported)
+  void* xchg_peer[MAX_PEERS] = {};              // peers' blocks mapped here (nullptr for this rank)
+  Xchg* xchg_dev = nullptr;
+  int xchg_world = 0, xchg_rank = 0, xchg_len = 0;
+  bool xchg_connected = false;
 };
+
+static void xchg_release(pdlp_engine* B);
 
 template <typename T>
 struct EngineT {
@@ -451,6 +459,7 @@ static void engine_destroy(pdlp_engine* B) {
     for (int b = 0; b < 2; ++b)
       if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
   if (E->h_scalars) cudaFreeHost(E->h_scalars);
+  xchg_release(B);
   for (void* p : E->allocs) cudaFreeAsync(p, B->stream);
   cudaStreamSynchronize(B->stream);
   delete E;
@@ -914,6 +923,119 @@ static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
   return 0;
 }
 
+// ---- peer-memory exchange: one iteration = SpMV -> exchange kernel -> rule -> primal (polls) -> dual ----
+static int xchg_seg(int L, int world) { return ((L + world - 1) / world + 1) / 2 * 2; }
+static size_t xchg_block_bytes(int L, int world) {
+  return sizeof(double) * (size_t)L + 16 * ((size_t)world * xchg_seg(L, world) + (size_t)L);
+}
+
+static void xchg_release(pdlp_engine* B) {
+  for (int p = 0; p < MAX_PEERS; ++p)
+    if (B->xchg_peer[p]) {
+      cudaIpcCloseMemHandle(B->xchg_peer[p]);
+      B->xchg_peer[p] = nullptr;
+    }
+  if (B->xchg_dev) cudaFree(B->xchg_dev);
+  if (B->xchg_block) cudaFree(B->xchg_block);
+  B->xchg_dev = nullptr;
+  B->xchg_block = nullptr;
+  B->xchg_connected = false;
+  cudaGetLastError();
+}
+
+static int xchg_create(pdlp_engine* B, int world, int rank, unsigned char* handle_out) {
+  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(PDLP_ERR_INVALID, "bad world / rank");
+  xchg_release(B);
+  const int L = ((int)B->n + 4 + 1) / 2 * 2;
+  B->xchg_world = world;
+  B->xchg_rank = rank;
+  B->xchg_len = L;
+  CU(cudaMalloc((void**)&B->xchg_block, xchg_block_bytes(L, world)));   // not from the async pool: IPC needs cudaMalloc
+  CU(cudaMemset(B->xchg_block, 0, xchg_block_bytes(L, world)));
+  CU(cudaMalloc((void**)&B->xchg_dev, sizeof(Xchg)));
+  cudaIpcMemHandle_t hd;
+  memset(&hd, 0, sizeof(hd));
+  if (world > 1) CU(cudaIpcGetMemHandle(&hd, B->xchg_block));
+  static_assert(sizeof(hd) == PDLP_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &hd, sizeof(hd));
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+template <typename T>
+static int xchg_connect(EngineT<T>* E, const unsigned char* handles) {
+  pdlp_engine* B = E->base;
+  if (!B->xchg_block) return fail(PDLP_ERR_INVALID, "pdlp_shard_exchange_create has not been called");
+  const int world = B->xchg_world, rank = B->xchg_rank, L = B->xchg_len;
+  const int seg = xchg_seg(L, world);
+  Xchg X;
+  memset(&X, 0, sizeof(X));
+  for (int p = 0; p < world; ++p) {
+    unsigned char* base = B->xchg_block;
+    if (p != rank) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, handles + (size_t)p * PDLP_IPC_HANDLE_BYTES, sizeof(hd));
+      void* ptr = nullptr;
+      CU(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+      B->xchg_peer[p] = ptr;
+      base = (unsigned char*)ptr;
+    }
+    X.recv[p] = (uint4*)(base + sizeof(double) * (size_t)L);
+    X.tot[p] = X.recv[p] + (size_t)world * seg;
+  }
+  X.part = (double*)B->xchg_block;
+  X.world = world;
+  X.rank = rank;
+  X.L = L;
+  X.seg = seg;
+  X.n = (int)B->n;
+  CU(cudaMemcpy(B->xchg_dev, &X, sizeof(X), cudaMemcpyHostToDevice));
+  Scalars h;
+  CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, B->stream));
+  CU(cudaStreamSynchronize(B->stream));
+  h.xchg_seq = 1;
+  h.xchg_error = 0;
+  CU(cudaMemcpyAsync(E->S, &h, sizeof(h), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaStreamSynchronize(B->stream));
+  B->xchg_connected = true;
+  return 0;
+}
+
+template <typename T>
+static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
+  if (!B->xchg_connected) return fail(PDLP_ERR_INVALID, "pdlp_shard_exchange_connect has not been called");
+  const int n = (int)B->n;
+  const int world = B->xchg_world, L = B->xchg_len;
+  double* part = (double*)B->xchg_block;
+  const uint4* tot = (const uint4*)(B->xchg_block + sizeof(double) * (size_t)L) + (size_t)world * xchg_seg(L, world);
+  // co-resident by construction: one CTA of 256 threads per SM at most
+  const int xg = std::max(1, std::min(B->sms, (L + 255) / 256));
+  for (int i = 0; i < n_iters; ++i) {
+    const bool save = save_prev && i == n_iters - 1;
+    ShardKtyOp<T> f{E->y, part, E->S, n};
+    CU(launch_stream(E->Kt, f, st));
+    xchg_kernel<<<xg, 256, 0, st>>>(B->xchg_dev, E->S);
+    xchg_rule_kernel<<<1, 1, 0, st>>>(B->xchg_dev, E->S);
+    if (save) {
+      shard_primal_kernel<T, true, true><<<E->ew_grid, 256, 0, st>>>(tot, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n,
+                                                                     E->S, E->ew_partials, E->ew_ticket);
+      DualOp<T, true, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+      CU(launch_stream(E->K, d, st));
+      B->have_prev = true;
+    } else {
+      shard_primal_kernel<T, false, true><<<E->ew_grid, 256, 0, st>>>(tot, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n,
+                                                                      E->S, E->ew_partials, E->ew_ticket);
+      DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+      CU(launch_stream(E->K, d, st));
+    }
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
 template <typename T>
 static int shard_check_begin(EngineT<T>* E, double* buf3, int have_prev) {
   pdlp_engine* B = E->base;
@@ -965,6 +1087,7 @@ static int shard_check_end(EngineT<T>* E, const double* buf1, pdlp_check* out) {
   Scalars h;
   CU(cudaMemcpyAsync(&h, E->S, sizeof(h), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (h.xchg_error) return fail(PDLP_ERR_CUDA, "peer-memory exchange timed out waiting for another rank");
   if (out) fill_check(out, h);
   return 0;
 }
@@ -1394,6 +1517,24 @@ extern "C" int pdlp_shard_step(pdlp_handle h, const double* buf, int save_previo
   CHECK_HANDLE(h);
   if (!buf) return fail(PDLP_ERR_INVALID, "null argument");
   return DISPATCH(h, shard_step, buf, save_previous);
+}
+extern "C" int pdlp_shard_exchange_create(pdlp_handle h, int world, int rank, unsigned char* handle_out) {
+  CHECK_HANDLE(h);
+  if (!handle_out) return fail(PDLP_ERR_INVALID, "null argument");
+  if (h->dtype != PDLP_F64) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
+  cudaSetDevice(h->device);
+  return xchg_create(h, world, rank, handle_out);
+}
+extern "C" int pdlp_shard_exchange_connect(pdlp_handle h, const unsigned char* handles) {
+  CHECK_HANDLE(h);
+  if (!handles) return fail(PDLP_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  return DISPATCH(h, xchg_connect, handles);
+}
+extern "C" int pdlp_shard_iterate_p2p(pdlp_handle h, int n_iters, int save_previous) {
+  CHECK_HANDLE(h);
+  if (n_iters < 0) return fail(PDLP_ERR_INVALID, "n_iters < 0");
+  return DISPATCH(h, shard_iterate_p2p, n_iters, save_previous);
 }
 extern "C" int pdlp_shard_rule_pack(pdlp_handle h, double* buf4) {
   CHECK_HANDLE(h);

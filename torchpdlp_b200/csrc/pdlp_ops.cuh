@@ -61,6 +61,9 @@ struct Scalars {
   double scratch[8];
   // fishnet: per point c^T x, l_dual^T max(lam,0), u_dual^T min(lam,0) for a batch of 8 points
   double batch[24];
+  // peer-memory exchange of the row-partitioned engine: sequence number of the next exchange, sticky error
+  unsigned long long xchg_seq;
+  int xchg_error, xchg_pad;
 };
 
 template <typename T>
@@ -627,17 +630,157 @@ __global__ void shard_rule_kernel(Scalars* S, const double* tail) {
   s.rule_pending = 0;
 }
 
+// ---------------------------------------------------------------------------
+// Peer-memory exchange (row-partitioned engine, NVLink / NVSwitch).  Every rank owns one block
+//   part[L] doubles | recv[world][seg] LL words | tot[L] LL words          (L = n + 4 rounded up to even)
+// mapped into every peer (CUDA IPC).  An LL word is 16 bytes {lo32, seq, hi32, seq}: one double travelling with
+// the sequence number of its exchange in both 8-byte halves, so a reader that sees seq twice has the value --
+// no flags, fences or acquire/release round trips, and nothing to reset (seq only grows).  One exchange is a
+// two-shot allreduce:
+//   ShardKtyOp (the K_g^T y_g SpMV)  writes part[] locally, its last CTA appends the pending step-rule partials
+//   xchg_kernel   phase 1: every rank stores segment s of its part[] into recv[rank] of rank s (NVLink stores)
+//                 phase 2: rank s polls its recv[*] slots, sums them in rank order and stores the sums into
+//                          tot[] of every rank (NVLink stores)
+//   xchg_rule_kernel / shard_primal_kernel poll tot[] locally.
+// Each segment is summed by exactly one rank, so all ranks see bit-identical totals.  The grid of xchg_kernel is
+// co-resident (phase 2 of one GPU waits for phase 1 of the others, never for its own later CTAs).  A poll that
+// lasts longer than XCHG_TIMEOUT_NS sets Scalars::xchg_error + stop instead of hanging the GPU.
+// ---------------------------------------------------------------------------
+constexpr int MAX_PEERS = 16;
+constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+struct Xchg {
+  uint4* recv[MAX_PEERS];      // every rank's recv area (world x seg words)
+  uint4* tot[MAX_PEERS];       // every rank's tot area (L words)
+  double* part;                // this rank's partial vector
+  int world, rank;
+  int L, seg;                  // padded length, elements per segment
+  int n, pad;
+};
+
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(seq),
+               "r"((unsigned int)(b >> 32)), "r"(seq)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ll_value(const uint4& v) {
+  return __longlong_as_double((long long)(((unsigned long long)v.z << 32) | (unsigned long long)v.x));
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// value of an LL word once it carries `seq`; on timeout (or after an earlier one) 0 and the sticky error
+__device__ inline double ll_wait(const uint4* p, unsigned int seq, Scalars* S) {
+  uint4 v = ll_load(p);
+  if (v.y == seq && v.w == seq) return ll_value(v);
+  unsigned long long t0 = 0;
+  unsigned int polls = 0;
+  for (;;) {
+    v = ll_load(p);
+    if (v.y == seq && v.w == seq) return ll_value(v);
+    if ((++polls & 0xffu) == 0) {
+      if (*(volatile int*)&S->xchg_error) return 0.0;
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > XCHG_TIMEOUT_NS) {
+        S->xchg_error = 1;
+        S->stop = 1;
+        return 0.0;
+      }
+    }
+  }
+}
+
+// rows of K_g^T: part[j] = (K_g^T y_g)[j]; the last CTA appends the pending step-rule partials
+template <typename T>
+struct ShardKtyOp {
+  using value_type = T;
+  using Gather = T;
+  using Ctx = NoCtx;
+  static constexpr int NV = 1;
+  static constexpr int NRED = 1;      // nothing to reduce: NRED > 0 buys the "last CTA" finalize
+  static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
+  const T* in;
+  double* out;                        // this rank's part[]
+  Scalars* S;
+  int n;
+  __device__ bool begin() { return true; }      // never skipped: the peers wait for this rank's data
+  __device__ T gather(int col) const { return ldg(in + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int) const { return Ctx{}; }
+  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) { out[r] = (double)acc[0]; }
+  __device__ void finalize(const double (&)[1]) {
+    const Scalars& s = *S;
+    out[n + 0] = s.rule_pending ? s.dy2 : 0.0;
+    out[n + 1] = s.rule_pending ? s.inter : 0.0;
+    out[n + 2] = 0.0;
+    out[n + 3] = 0.0;
+  }
+};
+
+__global__ void __launch_bounds__(256) xchg_kernel(const Xchg* Xp, Scalars* S) {
+  __shared__ Xchg X;
+  if (threadIdx.x == 0) X = *Xp;
+  __syncthreads();
+  const unsigned int seq = (unsigned int)S->xchg_seq;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  // phase 1: scatter my partial vector to the segment owners
+  for (int e = tid; e < X.L; e += nthr) {
+    const int s = e / X.seg;
+    ll_store(X.recv[s] + (size_t)X.rank * X.seg + (e - s * X.seg), X.part[e], seq);
+  }
+  // phase 2: reduce my segment in rank order, broadcast the sums
+  const int s0 = X.rank * X.seg;
+  const int len = max(0, min(X.L, s0 + X.seg) - s0);
+  const uint4* mine = X.recv[X.rank];
+  for (int i = tid; i < len; i += nthr) {
+    double a = 0.0;
+    for (int g = 0; g < X.world; ++g) a += ll_wait(mine + (size_t)g * X.seg + i, seq, S);
+    for (int p = 0; p < X.world; ++p) ll_store(X.tot[p] + s0 + i, a, seq);
+  }
+}
+
+// polls the tail of tot[], then the step rule of the pending iteration with the global norms
+__global__ void xchg_rule_kernel(const Xchg* X, Scalars* S) {
+  Scalars& s = *S;
+  const unsigned int seq = (unsigned int)s.xchg_seq;
+  const uint4* tail = X->tot[X->rank] + X->n;
+  const double dy2 = ll_wait(tail + 0, seq, S);
+  const double inter = ll_wait(tail + 1, seq, S);
+  s.xchg_seq = (unsigned long long)seq + 1;
+  if (!s.rule_pending) return;
+  s.dy2 = dy2;
+  s.inter = inter;
+  double w, next;
+  step_rule(s, s.dx2, dy2, inter, w, next);
+  commit_step(s, w, next);
+  s.rule_pending = 0;
+}
+
 // element-wise K1 epilogue on the allreduced K^T y (same arithmetic as PrimalOp::row_finish)
-template <typename T, bool SAVE_PREV>
-__global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
+// LL: kty points at LL words of the peer-memory exchange (polled until they carry seq) instead of doubles
+template <typename T, bool SAVE_PREV, bool LL = false>
+__global__ void shard_primal_kernel(const void* kty_, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
                                     Quad<T>* X4, int n, Scalars* S, double* partials, unsigned int* ticket) {
   if (S->stop) return;
   const T tau = (T)(S->eta / S->omega);
   const T wpend = (T)S->w_pending;
+  const unsigned int seq = (unsigned int)S->xchg_seq - 1u;     // the rule kernel already advanced it
   const int stride = gridDim.x * blockDim.x;
   double dx2 = 0.0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const T g = c[j] - (T)kty[j];
+    const T kty_j = LL ? (T)ll_wait(reinterpret_cast<const uint4*>(kty_) + j, seq, S)
+                       : (T) reinterpret_cast<const double*>(kty_)[j];
+    const T g = c[j] - kty_j;
     const T xo = xp[j].a;
     const T xn = clampv(xo - tau * g, l[j], u[j]);
     const T dx = xn - xo;

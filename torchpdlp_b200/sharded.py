@@ -5,7 +5,9 @@ the matching slices of y, q and the dual sums; x, c, l, u are replicated.  K_g x
 local; K^T y = sum_g K_g^T y_g is the single exchange of an iteration: one
 ``all_reduce`` of n + 4 doubles (the 4 extra slots carry the partial ||dy||^2 and
 dy^T K dx of the previous iteration, so the adaptive step rule needs no second
-collective).  The reference has no distributed code; the semantics are those of its
+collective).  With ``exchange="p2p"`` (GPUs of one node) that allreduce is not a host-issued collective at
+all: the K_g^T y_g kernel, a segment reduce/push kernel and the step-rule kernel talk through the peers' memory
+over NVLink (``pdlp_shard_iterate_p2p``, include/pdlp_b200.h).  The reference has no distributed code; the semantics are those of its
 single-device loop (primal_dual_hybrid_gradient.py:54-177), which the sharded run
 reproduces up to the summation order of the allreduce.
 
@@ -107,6 +109,29 @@ class GpuShardPrims:
     def sync(self):
         torch.cuda.synchronize(self.device)
 
+    IPC_HANDLE_BYTES = 64
+
+    def exchange_connect(self, group=None):
+        """Allocate this rank's exchange block, all-gather the CUDA IPC handles and map the peers' blocks."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        mine = (C.c_ubyte * self.IPC_HANDLE_BYTES)()
+        check(self.lib.pdlp_shard_exchange_create(self.h, world, rank, C.cast(mine, C.c_void_p)))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        if world > 1:
+            every = torch.empty(world * self.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, t, group=group)
+        else:
+            every = t
+        raw = bytes(every.cpu().tolist())
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        check(self.lib.pdlp_shard_exchange_connect(self.h, C.cast(buf, C.c_void_p)))
+        if world > 1:
+            dist.barrier(group=group)              # every rank has mapped every block before the first flag is raised
+
+    def iterate_p2p(self, n_iters, save_previous):
+        check(self.lib.pdlp_shard_iterate_p2p(self.h, int(n_iters), int(bool(save_previous))))
+
     def capture_block(self, fn):
         """Record fn() -- kernel launches of this engine interleaved with NCCL collectives -- into one CUDA
         graph; returns a callable that replays it on the current stream."""
@@ -125,9 +150,14 @@ class ShardedSolver:
     (``iterate``, ``restart_check``, ``state``), so ``primal_dual_hybrid_gradient.run_restart_loop`` is shared
     with the single-GPU path."""
 
-    def __init__(self, prims, group=None):
+    def __init__(self, prims, group=None, exchange="nccl"):
+        """exchange: "nccl" = one host-issued allreduce per iteration; "p2p" = the peer-memory kernels (GPUs of one
+        node; needs prims.exchange_connect)."""
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         self.p = prims
         self.group = group
+        self.exchange = exchange
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         n = prims.n
         self.buf = prims.buffer(n + 4)
@@ -143,6 +173,8 @@ class ShardedSolver:
         self._allreduce(t)
         self.q_norm, self.c_norm = float(t.item()) ** 0.5, c_norm
         prims.enable(self.q_norm, self.c_norm)
+        if exchange == "p2p":
+            prims.exchange_connect(group)
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -173,6 +205,10 @@ class ShardedSolver:
     def _iterate_eager(self, n_iters, save_previous):
         if save_previous:
             self._have_prev = True
+        if self.exchange == "p2p":                                 # the exchange happens inside the kernels
+            self.p.iterate_p2p(n_iters, save_previous)
+            self.collectives += n_iters
+            return
         for i in range(n_iters):
             self.p.kty(self.buf)
             self._allreduce(self.buf)                              # THE exchange: n + 4 doubles
@@ -243,8 +279,8 @@ class ShardedSolver:
         return x, y_local, prim_obj, k, n, j, status, time.time() - t0, sigma
 
 
-def build_rank_engine(K_local, m_ineq_local: int, c, q_local, l, u, device=None):
+def build_rank_engine(K_local, m_ineq_local: int, c, q_local, l, u, device=None, exchange="nccl"):
     """Engine on this rank's rows + the sharded driver."""
     from .engine import Engine
     eng = Engine(K_local, m_ineq_local, c, q_local, l, u, device=device, dtype=torch.float64)
-    return ShardedSolver(GpuShardPrims(eng))
+    return ShardedSolver(GpuShardPrims(eng), exchange=exchange)
