@@ -293,8 +293,8 @@ def run_engine(args):
 
 def run_sharded(args, world, rank, local, dev):
     """N > 1: the row-partitioned engine (torchpdlp_b200.sharded) on a weak-scaling LP: every rank holds one
-    config-2 row block (100k rows, 5M nnz) of a (N*100k) x 200k LP; x replicated; ONE NCCL allreduce of
-    n + 4 doubles per iteration.  value = N x iterations/s (row-block iterations per second), which equals
+    config-2 row block (100k rows, 5M nnz) of a (N*100k) x 200k LP; x replicated; one allreduce of n + 4
+    doubles per iteration, done by the iteration kernels through peer memory (PDLP_EXCHANGE=nccl: by NCCL).  value = N x iterations/s (row-block iterations per second), which equals
     the N = 1 metric when N = 1."""
     import torch.distributed as dist
     from torchpdlp_b200 import synthetic
@@ -316,7 +316,22 @@ def run_sharded(args, world, rank, local, dev):
         q = Kb @ x_feas
         mi = 0
     Kb = Kb.tocsr(); Kb.sort_indices()
-    solver = build_rank_engine(Kb, mi, c, q, l, u, device=dev)
+    # the exchange: peer-memory kernels over NVLink (default) or one host-issued NCCL allreduce per iteration
+    exchange = os.environ.get("PDLP_EXCHANGE", "p2p")
+    if exchange == "p2p":
+        try:
+            solver, ok = build_rank_engine(Kb, mi, c, q, l, u, device=dev, exchange="p2p"), 1.0
+        except Exception as exc:                        # e.g. CUDA IPC not permitted in this container
+            print(f"[rank {rank}] peer-memory exchange unavailable ({exc}); using NCCL", file=sys.stderr, flush=True)
+            solver, ok = None, 0.0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) < 1.0:                    # all ranks take the same path
+            if solver is not None:
+                solver.close()
+            exchange = "nccl"
+    if exchange != "p2p":
+        solver = build_rank_engine(Kb, mi, c, q, l, u, device=dev, exchange="nccl")
     torch.manual_seed(0)
     eta, omega, sigma = solver.initial_step(100)
     p = solver.p
@@ -363,7 +378,7 @@ def run_sharded(args, world, rank, local, dev):
     barrier()
     t0 = time.perf_counter()
     note("e2e build")
-    solver2 = build_rank_engine(Kb, mi, c, q, l, u, device=dev)
+    solver2 = build_rank_engine(Kb, mi, c, q, l, u, device=dev, exchange=exchange)
     torch.manual_seed(0)
     note("e2e solve")
     x, y, obj, k, nres, j, status, secs, sig = solver2.solve(adaptive=True, primal_update=True, max_kkt=20_000)
@@ -380,17 +395,19 @@ def run_sharded(args, world, rank, local, dev):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"row-partitioned LP m={world * m_blk} n={n} nnz={world * Kb.nnz}: one config-2 row block "
                                    f"(100k rows, 5M nnz) per GPU, fp64, restarts + adaptive step + primal weight",
-                       "step": "40 PDHG iterations + restart test", "parallelism": f"row partition over {world} GPUs, "
-                       f"1 NCCL allreduce of n+4 doubles per iteration", "value_is": "n_gpus x iterations/s",
+                       "step": "40 PDHG iterations + restart test", "parallelism": f"row partition over {world} GPUs, " + (
+                           "allreduce of n+4 doubles per iteration inside the iteration kernels (peer memory over NVLink, "
+                           "LL protocol)" if exchange == "p2p" else "1 NCCL allreduce of n+4 doubles per iteration"),
+                       "exchange": exchange, "value_is": "n_gpus x iterations/s",
                        "l2": "per-GPU working set ~140 MB > 126 MB L2; no explicit flush"},
             "us_per_iteration": 1e3 * ms / iters,
             "iteration_roofline_frac": b_iter_rank / (ms * 1e-3 / iters) / 1e9 / peak,
-            "gpu_launches": (5 * RESTART_PERIOD + 14) * args.steps, "clocks": clocks,
+            "gpu_launches": ((3 if exchange == "p2p" else 5) * RESTART_PERIOD + 14) * args.steps, "clocks": clocks,
             "e2e": {"value": world * k / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(Kb.nnz * 12 + (m_blk + 1) * 4 + 8 * (3 * n + m_blk)),
                     "d2h_bytes_per_step": x_host.numel() * 8 + 64,
                     "what": f"whole sharded solve from host data: {status} k={k} n={nres}, {e2e_s:.3f} s"},
-            "roofline": {"bound": "hbm", "kernel": "per-GPU iteration (4 kernels + allreduce)", "achieved":
+            "roofline": {"bound": "hbm", "kernel": "per-GPU iteration (" + ("3 kernels, exchange fused" if exchange == "p2p" else "4 kernels + allreduce") + ")", "achieved":
                          b_iter_rank / (ms * 1e-3 / iters) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b_iter_rank / (ms * 1e-3 / iters) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
             "cpu_baseline": None,

@@ -1010,24 +1010,31 @@ static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
   const int n = (int)B->n;
   const int world = B->xchg_world, L = B->xchg_len;
   double* part = (double*)B->xchg_block;
-  const uint4* tot = (const uint4*)(B->xchg_block + sizeof(double) * (size_t)L) + (size_t)world * xchg_seg(L, world);
-  // co-resident by construction: one CTA of 256 threads per SM at most
-  const int xg = std::max(1, std::min(B->sms, (L + 255) / 256));
+  (void)world; (void)L;
+  const int xg = std::min(E->ew_grid, B->sms * 2);      // co-resident: at most 2 CTAs of 256 threads per SM
   for (int i = 0; i < n_iters; ++i) {
     const bool save = save_prev && i == n_iters - 1;
     ShardKtyOp<T> f{E->y, part, E->S, n};
     CU(launch_stream(E->Kt, f, st));
-    xchg_kernel<<<xg, 256, 0, st>>>(B->xchg_dev, E->S);
-    xchg_rule_kernel<<<1, 1, 0, st>>>(B->xchg_dev, E->S);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(xg);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const Xchg* xd = B->xchg_dev;
     if (save) {
-      shard_primal_kernel<T, true, true><<<E->ew_grid, 256, 0, st>>>(tot, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n,
-                                                                     E->S, E->ew_partials, E->ew_ticket);
+      CU(cudaLaunchKernelEx(&cfg, xchg_primal_kernel<T, true>, xd, (const T*)E->c, (const T*)E->l, (const T*)E->u, E->xp,
+                            E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
       DualOp<T, true, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
       CU(launch_stream(E->K, d, st));
       B->have_prev = true;
     } else {
-      shard_primal_kernel<T, false, true><<<E->ew_grid, 256, 0, st>>>(tot, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n,
-                                                                      E->S, E->ew_partials, E->ew_ticket);
+      CU(cudaLaunchKernelEx(&cfg, xchg_primal_kernel<T, false>, xd, (const T*)E->c, (const T*)E->l, (const T*)E->u, E->xp,
+                            E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
       DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
       CU(launch_stream(E->K, d, st));
     }

@@ -104,13 +104,11 @@ template <typename P> __device__ __forceinline__ auto ldg_keep(const P* p) { ret
 
 // The step-size rule: step.py:96-115 (adaptive) / :40 (fixed).  Increments k (pdlp :76 counts the iteration
 // before the rule reads it) and returns the averaging weight of the new iterate and the next step size.
-__device__ inline void step_rule(Scalars& s, double dx2, double dy2, double inter, double& w, double& next) {
-  const long long k = s.k + 1;
-  s.k = k;
-  const double eta = s.eta, omega = s.omega;
+__device__ inline void rule_values(int adaptive, long long k, double eta, double omega, double dx2, double dy2,
+                                   double inter, double& w, double& next) {   // k: already incremented
   w = eta;
   next = eta;
-  if (s.adaptive) {
+  if (adaptive) {
     const double den = 2.0 * inter;
     double eta_bar, t1;
     if (den != 0.0) {
@@ -124,6 +122,11 @@ __device__ inline void step_rule(Scalars& s, double dx2, double dy2, double inte
     const double ep = fmin(t1, t2);
     if (eta <= eta_bar) { w = eta; next = ep; } else { w = ep; next = ep; }
   }
+}
+__device__ inline void step_rule(Scalars& s, double dx2, double dy2, double inter, double& w, double& next) {
+  const long long k = s.k + 1;
+  s.k = k;
+  rule_values(s.adaptive, k, s.eta, s.omega, dx2, dy2, inter, w, next);
 }
 // averaging bookkeeping of pdlp :104-112 (the weight is folded into the sums by the next kernels that read the iterate)
 __device__ inline void commit_step(Scalars& s, double w, double next) {
@@ -809,6 +812,104 @@ __global__ void shard_primal_kernel(const void* kty_, const T* c, const T* l, co
     double a = 0.0;
     for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&partials[b]);
     S->dx2 = a;
+    *ticket = 0u;
+  }
+}
+
+// The exchange and the primal update in ONE kernel (pdlp_shard_iterate_p2p): phases 1-2 of xchg_kernel, then every
+// CTA polls the tail of tot[], evaluates the pending step rule for itself (read-only on Scalars), polls its share
+// of tot[] and updates x; the last CTA -- every reader of Scalars is done by then -- commits the rule, ||dx||^2 and
+// the sequence number.  The grid must be co-resident (<= 2 CTAs of 256 threads per SM).
+template <typename T, bool SAVE_PREV>
+__global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const T* c, const T* l, const T* u,
+                                                          Pair<T>* xp, T* xsum, Quad<T>* X4, Scalars* S,
+                                                          double* partials, unsigned int* ticket) {
+  __shared__ Xchg X;
+  __shared__ double sh[32];
+  __shared__ double s_rule[4];      // eta (post rule), w_pending (post rule), dy2, inter
+  __shared__ double s_w, s_next;
+  __shared__ int s_last, s_stop, s_pending;
+  if (threadIdx.x == 0) X = *Xp;
+  // programmatic dependent launch: resident while the SpMV before it drains, the dual kernel after it may prefetch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+  const unsigned int seq = (unsigned int)S->xchg_seq;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  for (int e = tid; e < X.L; e += nthr) {
+    const int s = e / X.seg;
+    ll_store(X.recv[s] + (size_t)X.rank * X.seg + (e - s * X.seg), X.part[e], seq);
+  }
+  const int s0 = X.rank * X.seg;
+  const int len = max(0, min(X.L, s0 + X.seg) - s0);
+  const uint4* mine = X.recv[X.rank];
+  for (int i = tid; i < len; i += nthr) {
+    double a = 0.0;
+    for (int g = 0; g < X.world; ++g) a += ll_wait(mine + (size_t)g * X.seg + i, seq, S);
+    for (int p = 0; p < X.world; ++p) ll_store(X.tot[p] + s0 + i, a, seq);
+  }
+  const uint4* tot = X.tot[X.rank];
+  if (threadIdx.x == 0) {
+    const double dy2 = ll_wait(tot + X.n + 0, seq, S);
+    const double inter = ll_wait(tot + X.n + 1, seq, S);
+    const int pending = S->rule_pending;
+    double eta = S->eta, wp = S->w_pending, w = 0.0, next = 0.0;
+    if (pending) {
+      rule_values(S->adaptive, S->k + 1, eta, S->omega, S->dx2, dy2, inter, w, next);
+      eta = next;
+      wp = w;
+    }
+    s_rule[0] = eta; s_rule[1] = wp; s_rule[2] = dy2; s_rule[3] = inter;
+    s_w = w; s_next = next;
+    s_pending = pending;
+    s_stop = S->stop;
+  }
+  __syncthreads();
+  double dx2 = 0.0;
+  if (!s_stop) {
+    const T tau = (T)(s_rule[0] / S->omega);
+    const T wpend = (T)s_rule[1];
+    for (int j = tid; j < X.n; j += nthr) {
+      const T g = c[j] - (T)ll_wait(tot + j, seq, S);
+      const T xo = xp[j].a;
+      const T xn = clampv(xo - tau * g, l[j], u[j]);
+      const T dx = xn - xo;
+      xp[j] = Pair<T>{xn, dx};
+      xsum[j] += wpend * xo;
+      if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
+      dx2 += (double)dx * (double)dx;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+  if (lane == 0) sh[warp] = dx2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+    partials[blockIdx.x] = a;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    Scalars& s = *S;
+    if (s_pending) {          // commit the rule every CTA evaluated (shard_rule_kernel's arithmetic)
+      s.k += 1;
+      s.dy2 = s_rule[2];
+      s.inter = s_rule[3];
+      commit_step(s, s_w, s_next);
+      s.rule_pending = 0;
+    }
+    if (!s_stop) {
+      double a = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&partials[b]);
+      s.dx2 = a;
+    }
+    s.xchg_seq = (unsigned long long)seq + 1;
     *ticket = 0u;
   }
 }
