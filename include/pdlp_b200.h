@@ -237,19 +237,24 @@ int pdlp_shard_check_decide(pdlp_handle h, const double* buf9, int force, double
 int pdlp_shard_check_end(pdlp_handle h, const double* buf1, pdlp_check* host_out);
 
 /* Peer-memory exchange (NVLink / NVSwitch, one process per GPU on one node): replaces the host-issued allreduce of
- * the iteration by kernels that read and write the peers' buffers directly.
+ * the iteration by kernels that read and write the peers' buffers directly.  Data travels as 16-byte LL words
+ * {lo32, seq, hi32, seq} (value + sequence number of the exchange), so there are no flags or fences to wait for.
  *   pdlp_shard_exchange_create   allocates this rank's exchange block and returns its CUDA IPC handle
  *                                (PDLP_IPC_HANDLE_BYTES bytes; all-gather them over any host transport)
  *   pdlp_shard_exchange_connect  maps the peers' blocks; handles = world x PDLP_IPC_HANDLE_BYTES, rank order
- *   pdlp_shard_iterate_p2p       n_iters iterations, per iteration: K_g^T y_g SpMV whose last CTA raises a flag on
- *                                every peer -> segment reduce over NVLink loads + push of the sums into every peer
- *                                -> step rule + primal update + local dual kernel.  Capturable in a CUDA graph.
- * Every rank must enqueue the same calls; a rank that waits > 20 s for a peer stops and the next
- * pdlp_shard_check_end reports the error.  The restart test keeps its host-issued collectives.        */
+ *   pdlp_shard_iterate_p2p       n_iters iterations of three kernels each: the K_g^T y_g SpMV; ONE kernel that
+ *                                stores its segments into the owners' memory, sums the owned segment in rank order,
+ *                                stores the sums into every peer, evaluates the step rule and does the primal
+ *                                update as the sums arrive; the local dual kernel.  Capturable in a CUDA graph.
+ *   pdlp_shard_allreduce_p2p     in-place sum of `count` device doubles over the same block (the small collectives
+ *                                of the restart test and of the power iteration)
+ * Every rank must enqueue the same calls in the same order; a rank that waits > 20 s for a peer stops and the next
+ * pdlp_shard_check_end reports the error.                                                             */
 #define PDLP_IPC_HANDLE_BYTES 64
 int pdlp_shard_exchange_create(pdlp_handle h, int world, int rank, unsigned char* handle_out);
 int pdlp_shard_exchange_connect(pdlp_handle h, const unsigned char* handles);
 int pdlp_shard_iterate_p2p(pdlp_handle h, int n_iters, int save_previous);
+int pdlp_shard_allreduce_p2p(pdlp_handle h, double* buf, int64_t count);
 
 /* ---- whole solve --------------------------------------------------------------
  * pdlp_algorithm (primal_dual_hybrid_gradient.py:7-181) driven from C++:

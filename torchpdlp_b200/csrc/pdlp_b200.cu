@@ -1002,19 +1002,30 @@ static int xchg_connect(EngineT<T>* E, const unsigned char* handles) {
 }
 
 template <typename T>
+static int shard_allreduce_p2p(EngineT<T>* E, double* buf, int64_t count) {
+  pdlp_engine* B = E->base;
+  if (!B->xchg_connected) return fail(PDLP_ERR_INVALID, "pdlp_shard_exchange_connect has not been called");
+  const int64_t cap = B->xchg_len;
+  for (int64_t off = 0; off < count; off += cap) {       // longer vectors go through the block in chunks
+    const int c = (int)std::min<int64_t>(cap, count - off);
+    const int grid = std::max(1, std::min(B->sms * 2, (c + 255) / 256));
+    xchg_allreduce_kernel<<<grid, 256, 0, B->stream>>>(B->xchg_dev, E->S, buf + off, c, E->ew_ticket);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+template <typename T>
 static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
   pdlp_engine* B = E->base;
   cudaStream_t st = B->stream;
   if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
   if (!B->xchg_connected) return fail(PDLP_ERR_INVALID, "pdlp_shard_exchange_connect has not been called");
-  const int n = (int)B->n;
-  const int world = B->xchg_world, L = B->xchg_len;
   double* part = (double*)B->xchg_block;
-  (void)world; (void)L;
   const int xg = std::min(E->ew_grid, B->sms * 2);      // co-resident: at most 2 CTAs of 256 threads per SM
   for (int i = 0; i < n_iters; ++i) {
     const bool save = save_prev && i == n_iters - 1;
-    ShardKtyOp<T> f{E->y, part, E->S, n};
+    ShardKtyOp<T> f{E->y, part, E->S};
     CU(launch_stream(E->Kt, f, st));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(xg);
@@ -1542,6 +1553,11 @@ extern "C" int pdlp_shard_iterate_p2p(pdlp_handle h, int n_iters, int save_previ
   CHECK_HANDLE(h);
   if (n_iters < 0) return fail(PDLP_ERR_INVALID, "n_iters < 0");
   return DISPATCH(h, shard_iterate_p2p, n_iters, save_previous);
+}
+extern "C" int pdlp_shard_allreduce_p2p(pdlp_handle h, double* buf, int64_t count) {
+  CHECK_HANDLE(h);
+  if (!buf || count < 0) return fail(PDLP_ERR_INVALID, "bad argument");
+  return DISPATCH(h, shard_allreduce_p2p, buf, count);
 }
 extern "C" int pdlp_shard_rule_pack(pdlp_handle h, double* buf4) {
   CHECK_HANDLE(h);

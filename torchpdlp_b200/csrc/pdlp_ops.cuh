@@ -635,10 +635,12 @@ __global__ void shard_rule_kernel(Scalars* S, const double* tail) {
 
 // ---------------------------------------------------------------------------
 // Peer-memory exchange (row-partitioned engine, NVLink / NVSwitch).  Every rank owns one block
-//   part[L] doubles | recv[world][seg] LL words | tot[L] LL words          (L = n + 4 rounded up to even)
+//   part[L] doubles | recv[world][seg] LL words | tot[L] LL words          (L = 4 + n rounded up to even)
+// where element 0..3 of the exchanged vector is the step-rule tail (it is needed first) and element 4 + j is column j,
 // mapped into every peer (CUDA IPC).  An LL word is 16 bytes {lo32, seq, hi32, seq}: one double travelling with
 // the sequence number of its exchange in both 8-byte halves, so a reader that sees seq twice has the value --
-// no flags, fences or acquire/release round trips, and nothing to reset (seq only grows).  One exchange is a
+// no flags, fences or acquire/release round trips, and nothing to reset (seq only grows).  (The accessors are
+// volatile asm without a memory clobber: ordered among themselves, but ordinary loads may be scheduled around them.)  One exchange is a
 // two-shot allreduce:
 //   ShardKtyOp (the K_g^T y_g SpMV)  writes part[] locally, its last CTA appends the pending step-rule partials
 //   xchg_kernel   phase 1: every rank stores segment s of its part[] into recv[rank] of rank s (NVLink stores)
@@ -650,6 +652,7 @@ __global__ void shard_rule_kernel(Scalars* S, const double* tail) {
 // lasts longer than XCHG_TIMEOUT_NS sets Scalars::xchg_error + stop instead of hanging the GPU.
 // ---------------------------------------------------------------------------
 constexpr int MAX_PEERS = 16;
+constexpr int XCHG_TAIL = 4;
 constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 struct Xchg {
   uint4* recv[MAX_PEERS];      // every rank's recv area (world x seg words)
@@ -663,12 +666,11 @@ struct Xchg {
 __device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(seq),
-               "r"((unsigned int)(b >> 32)), "r"(seq)
-               : "memory");
+               "r"((unsigned int)(b >> 32)), "r"(seq));
 }
 __device__ __forceinline__ uint4 ll_load(const uint4* p) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double ll_value(const uint4& v) {
@@ -679,14 +681,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// cooperative copy of the descriptor into shared memory (it is read by every thread afterwards)
+__device__ __forceinline__ void xchg_load(Xchg& X, const Xchg* Xp) {
+  static_assert(sizeof(Xchg) % 8 == 0, "Xchg is copied in 8-byte words");
+  if (threadIdx.x < sizeof(Xchg) / 8)
+    reinterpret_cast<unsigned long long*>(&X)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(Xp)[threadIdx.x];
+}
 // value of an LL word once it carries `seq`; on timeout (or after an earlier one) 0 and the sticky error
-__device__ inline double ll_wait(const uint4* p, unsigned int seq, Scalars* S) {
-  uint4 v = ll_load(p);
-  if (v.y == seq && v.w == seq) return ll_value(v);
+__device__ __noinline__ double ll_wait_slow(const uint4* p, unsigned int seq, Scalars* S) {
   unsigned long long t0 = 0;
   unsigned int polls = 0;
   for (;;) {
-    v = ll_load(p);
+    const uint4 v = ll_load(p);
     if (v.y == seq && v.w == seq) return ll_value(v);
     if ((++polls & 0xffu) == 0) {
       if (*(volatile int*)&S->xchg_error) return 0.0;
@@ -700,6 +706,14 @@ __device__ inline double ll_wait(const uint4* p, unsigned int seq, Scalars* S) {
     }
   }
 }
+// v: a speculative load of *p issued earlier (the common case: it already carries seq)
+__device__ __forceinline__ double ll_wait(const uint4* p, unsigned int seq, Scalars* S, const uint4& v) {
+  if (v.y == seq && v.w == seq) return ll_value(v);
+  return ll_wait_slow(p, seq, S);
+}
+__device__ __forceinline__ double ll_wait(const uint4* p, unsigned int seq, Scalars* S) {
+  return ll_wait(p, seq, S, ll_load(p));
+}
 
 // rows of K_g^T: part[j] = (K_g^T y_g)[j]; the last CTA appends the pending step-rule partials
 template <typename T>
@@ -712,78 +726,97 @@ struct ShardKtyOp {
   static constexpr int UDIV = 1;
   static constexpr int PIPE = 1;
   const T* in;
-  double* out;                        // this rank's part[]
+  double* part;                       // this rank's part[]: tail, then the columns
   Scalars* S;
-  int n;
   __device__ bool begin() { return true; }      // never skipped: the peers wait for this rank's data
   __device__ T gather(int col) const { return ldg(in + col); }
   __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
   __device__ Ctx row_load(int) const { return Ctx{}; }
-  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) { out[r] = (double)acc[0]; }
+  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) { part[XCHG_TAIL + r] = (double)acc[0]; }
   __device__ void finalize(const double (&)[1]) {
     const Scalars& s = *S;
-    out[n + 0] = s.rule_pending ? s.dy2 : 0.0;
-    out[n + 1] = s.rule_pending ? s.inter : 0.0;
-    out[n + 2] = 0.0;
-    out[n + 3] = 0.0;
+    part[0] = s.rule_pending ? s.dy2 : 0.0;
+    part[1] = s.rule_pending ? s.inter : 0.0;
+    part[2] = 0.0;
+    part[3] = 0.0;
   }
 };
 
-__global__ void __launch_bounds__(256) xchg_kernel(const Xchg* Xp, Scalars* S) {
-  __shared__ Xchg X;
-  if (threadIdx.x == 0) X = *Xp;
-  __syncthreads();
-  const unsigned int seq = (unsigned int)S->xchg_seq;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nthr = gridDim.x * blockDim.x;
-  // phase 1: scatter my partial vector to the segment owners
-  for (int e = tid; e < X.L; e += nthr) {
-    const int s = e / X.seg;
-    ll_store(X.recv[s] + (size_t)X.rank * X.seg + (e - s * X.seg), X.part[e], seq);
+// phases 1 and 2 of an exchange of src[0 .. count): scatter to the owners, reduce the owned segment, broadcast.
+// All loads of a batch are issued before the first one is inspected (volatile loads are not reordered by the
+// compiler, so a loop of ll_wait would pay one L2 / NVLink latency per peer).
+__device__ __forceinline__ void xchg_scatter_reduce(const Xchg& X, const double* src, int count, unsigned int seq,
+                                                    Scalars* S, int tid, int nthr) {
+  constexpr int NB = 4;
+  for (int e0 = tid; e0 < count; e0 += NB * nthr) {
+    double v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (e0 + b * nthr < count) v[b] = src[e0 + b * nthr];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int e = e0 + b * nthr;
+      if (e < count) {
+        const int s = e / X.seg;
+        ll_store(X.recv[s] + (size_t)X.rank * X.seg + (e - s * X.seg), v[b], seq);
+      }
+    }
   }
-  // phase 2: reduce my segment in rank order, broadcast the sums
   const int s0 = X.rank * X.seg;
-  const int len = max(0, min(X.L, s0 + X.seg) - s0);
+  const int len = max(0, min(count, s0 + X.seg) - s0);
   const uint4* mine = X.recv[X.rank];
   for (int i = tid; i < len; i += nthr) {
     double a = 0.0;
-    for (int g = 0; g < X.world; ++g) a += ll_wait(mine + (size_t)g * X.seg + i, seq, S);
+    for (int g0 = 0; g0 < X.world; g0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (g0 + j < X.world) v[j] = ll_load(mine + (size_t)(g0 + j) * X.seg + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (g0 + j < X.world) a += ll_wait(mine + (size_t)(g0 + j) * X.seg + i, seq, S, v[j]);     // rank order
+    }
     for (int p = 0; p < X.world; ++p) ll_store(X.tot[p] + s0 + i, a, seq);
   }
 }
 
-// polls the tail of tot[], then the step rule of the pending iteration with the global norms
-__global__ void xchg_rule_kernel(const Xchg* X, Scalars* S) {
-  Scalars& s = *S;
-  const unsigned int seq = (unsigned int)s.xchg_seq;
-  const uint4* tail = X->tot[X->rank] + X->n;
-  const double dy2 = ll_wait(tail + 0, seq, S);
-  const double inter = ll_wait(tail + 1, seq, S);
-  s.xchg_seq = (unsigned long long)seq + 1;
-  if (!s.rule_pending) return;
-  s.dy2 = dy2;
-  s.inter = inter;
-  double w, next;
-  step_rule(s, s.dx2, dy2, inter, w, next);
-  commit_step(s, w, next);
-  s.rule_pending = 0;
+// stand-alone allreduce (sum) of buf[0 .. count) over the same exchange block, count <= L: the small collectives of
+// the restart test and the power iteration (pdlp_shard_allreduce_p2p).  Co-resident grid; the last CTA advances seq.
+__global__ void __launch_bounds__(256) xchg_allreduce_kernel(const Xchg* Xp, Scalars* S, double* buf, int count,
+                                                             unsigned int* ticket) {
+  __shared__ Xchg X;
+  __shared__ int s_last;
+  xchg_load(X, Xp);
+  __syncthreads();
+  const unsigned int seq = (unsigned int)S->xchg_seq;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthr = gridDim.x * blockDim.x;
+  xchg_scatter_reduce(X, buf, count, seq, S, tid, nthr);
+  const uint4* tot = X.tot[X.rank];
+  for (int e = tid; e < count; e += nthr) buf[e] = ll_wait(tot + e, seq, S);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    S->xchg_seq = (unsigned long long)seq + 1;
+    *ticket = 0u;
+  }
 }
 
 // element-wise K1 epilogue on the allreduced K^T y (same arithmetic as PrimalOp::row_finish)
-// LL: kty points at LL words of the peer-memory exchange (polled until they carry seq) instead of doubles
-template <typename T, bool SAVE_PREV, bool LL = false>
-__global__ void shard_primal_kernel(const void* kty_, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
+template <typename T, bool SAVE_PREV>
+__global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
                                     Quad<T>* X4, int n, Scalars* S, double* partials, unsigned int* ticket) {
   if (S->stop) return;
   const T tau = (T)(S->eta / S->omega);
   const T wpend = (T)S->w_pending;
-  const unsigned int seq = (unsigned int)S->xchg_seq - 1u;     // the rule kernel already advanced it
   const int stride = gridDim.x * blockDim.x;
   double dx2 = 0.0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const T kty_j = LL ? (T)ll_wait(reinterpret_cast<const uint4*>(kty_) + j, seq, S)
-                       : (T) reinterpret_cast<const double*>(kty_)[j];
-    const T g = c[j] - kty_j;
+    const T g = c[j] - (T)kty[j];
     const T xo = xp[j].a;
     const T xn = clampv(xo - tau * g, l[j], u[j]);
     const T dx = xn - xo;
@@ -829,7 +862,7 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
   __shared__ double s_rule[4];      // eta (post rule), w_pending (post rule), dy2, inter
   __shared__ double s_w, s_next;
   __shared__ int s_last, s_stop, s_pending;
-  if (threadIdx.x == 0) X = *Xp;
+  xchg_load(X, Xp);
   // programmatic dependent launch: resident while the SpMV before it drains, the dual kernel after it may prefetch
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -837,22 +870,12 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
   const unsigned int seq = (unsigned int)S->xchg_seq;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthr = gridDim.x * blockDim.x;
-  for (int e = tid; e < X.L; e += nthr) {
-    const int s = e / X.seg;
-    ll_store(X.recv[s] + (size_t)X.rank * X.seg + (e - s * X.seg), X.part[e], seq);
-  }
-  const int s0 = X.rank * X.seg;
-  const int len = max(0, min(X.L, s0 + X.seg) - s0);
-  const uint4* mine = X.recv[X.rank];
-  for (int i = tid; i < len; i += nthr) {
-    double a = 0.0;
-    for (int g = 0; g < X.world; ++g) a += ll_wait(mine + (size_t)g * X.seg + i, seq, S);
-    for (int p = 0; p < X.world; ++p) ll_store(X.tot[p] + s0 + i, a, seq);
-  }
+  xchg_scatter_reduce(X, X.part, X.L, seq, S, tid, nthr);
   const uint4* tot = X.tot[X.rank];
   if (threadIdx.x == 0) {
-    const double dy2 = ll_wait(tot + X.n + 0, seq, S);
-    const double inter = ll_wait(tot + X.n + 1, seq, S);
+    const uint4 v0 = ll_load(tot + 0), v1 = ll_load(tot + 1);
+    const double dy2 = ll_wait(tot + 0, seq, S, v0);
+    const double inter = ll_wait(tot + 1, seq, S, v1);
     const int pending = S->rule_pending;
     double eta = S->eta, wp = S->w_pending, w = 0.0, next = 0.0;
     if (pending) {
@@ -870,15 +893,34 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
   if (!s_stop) {
     const T tau = (T)(s_rule[0] / S->omega);
     const T wpend = (T)s_rule[1];
-    for (int j = tid; j < X.n; j += nthr) {
-      const T g = c[j] - (T)ll_wait(tot + j, seq, S);
-      const T xo = xp[j].a;
-      const T xn = clampv(xo - tau * g, l[j], u[j]);
-      const T dx = xn - xo;
-      xp[j] = Pair<T>{xn, dx};
-      xsum[j] += wpend * xo;
-      if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
-      dx2 += (double)dx * (double)dx;
+    const uint4* col = tot + XCHG_TAIL;
+    constexpr int NB = 4;
+    for (int j0 = tid; j0 < X.n; j0 += NB * nthr) {
+      uint4 v[NB];
+      T cj[NB], lj[NB], uj[NB], sj[NB];
+      Pair<T> pj[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int j = j0 + b * nthr;
+        if (j < X.n) {
+          v[b] = ll_load(col + j);
+          cj[b] = c[j]; lj[b] = l[j]; uj[b] = u[j]; sj[b] = xsum[j]; pj[b] = xp[j];
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int j = j0 + b * nthr;
+        if (j < X.n) {
+          const T g = cj[b] - (T)ll_wait(col + j, seq, S, v[b]);
+          const T xo = pj[b].a;
+          const T xn = clampv(xo - tau * g, lj[b], uj[b]);
+          const T dx = xn - xo;
+          xp[j] = Pair<T>{xn, dx};
+          xsum[j] = sj[b] + wpend * xo;
+          if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
+          dx2 += (double)dx * (double)dx;
+        }
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -129,6 +129,9 @@ class GpuShardPrims:
         if world > 1:
             dist.barrier(group=group)              # every rank has mapped every block before the first flag is raised
 
+    def allreduce_p2p(self, t):
+        check(self.lib.pdlp_shard_allreduce_p2p(self.h, t.data_ptr(), t.numel()))
+
     def iterate_p2p(self, n_iters, save_previous):
         check(self.lib.pdlp_shard_iterate_p2p(self.h, int(n_iters), int(bool(save_previous))))
 
@@ -168,6 +171,7 @@ class ShardedSolver:
         self.collectives = 0
         self._graphs = {}
         self._have_prev = False
+        self._p2p_ready = False
         q2, c_norm = prims.local_q_sumsq()
         t = torch.tensor([q2], dtype=torch.float64, device=self.buf.device)
         self._allreduce(t)
@@ -175,9 +179,12 @@ class ShardedSolver:
         prims.enable(self.q_norm, self.c_norm)
         if exchange == "p2p":
             prims.exchange_connect(group)
+            self._p2p_ready = True
 
     def _allreduce(self, t):
-        if self.world > 1:
+        if self._p2p_ready and t.dtype == torch.float64 and t.is_contiguous():
+            self.p.allreduce_p2p(t)                                # also with one rank: same kernels, same bits
+        elif self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         self.collectives += 1
 
