@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -61,8 +62,21 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
   // sigma is adaptive: the smallest window (starting from the requested one) whose padded size stays within 5 % of
   // the nonzeros -- heavy-tailed row lengths need a wide window (config 4: 1.74x padding at 1024 rows, 1.05x at
   // 16384), uniform ones keep the narrow window and with it the locality of the row epilogue.
+  // (lengths are small integers, <= long_row: histograms and a stable counting sort instead of comparison sorts --
+  // the planner is on the end-to-end path of every solve)
+  std::vector<int> hist, tmp;
+  auto window_hist = [&](size_t w0, size_t w1, int& lo, int& hi) {
+    lo = 0x7fffffff;
+    hi = 0;
+    for (size_t i = w0; i < w1; ++i) {
+      const int L = len(order[i]);
+      lo = std::min(lo, L);
+      hi = std::max(hi, L);
+    }
+    hist.assign((size_t)(hi - lo + 1), 0);
+    for (size_t i = w0; i < w1; ++i) ++hist[(size_t)(len(order[i]) - lo)];
+  };
   {
-    std::vector<int> tmp;
     long long nnz_short = 0;
     for (int r : order) nnz_short += len(r);
     int best = sigma;
@@ -71,18 +85,32 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
       long long padded = 0;
       for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)cand) {
         const size_t w1 = std::min(order.size(), w0 + (size_t)cand);
-        tmp.clear();
-        for (size_t i = w0; i < w1; ++i) tmp.push_back(len(order[i]));
-        std::sort(tmp.begin(), tmp.end(), std::greater<int>());
-        for (size_t i = 0; i < tmp.size(); i += 32) padded += 32LL * tmp[i];
+        int lo, hi;
+        window_hist(w0, w1, lo, hi);
+        size_t placed = 0;      // rows of the window already placed in descending order; a slice starts every 32
+        for (int L = hi; L >= lo; --L) {
+          const size_t cnt = (size_t)hist[(size_t)(L - lo)];
+          if (!cnt) continue;
+          padded += 32LL * L * (long long)((placed + cnt + 31) / 32 - (placed + 31) / 32);
+          placed += cnt;
+        }
       }
       if (padded <= nnz_short + nnz_short / 20 || (size_t)cand >= order.size()) break;
     }
     sigma = best;
   }
-  for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {
+  for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {     // stable, descending by length
     const size_t w1 = std::min(order.size(), w0 + (size_t)sigma);
-    std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return len(a) > len(b); });
+    int lo, hi;
+    window_hist(w0, w1, lo, hi);
+    int run = 0;
+    for (int L = hi; L >= lo; --L) {                                  // hist -> start offset of each length
+      const int cnt = hist[(size_t)(L - lo)];
+      hist[(size_t)(L - lo)] = run;
+      run += cnt;
+    }
+    tmp.assign(order.begin() + w0, order.begin() + w1);
+    for (int r : tmp) order[w0 + (size_t)hist[(size_t)(len(r) - lo)]++] = r;
   }
   while (order.size() % 32) order.push_back(-1);
   P.perm = order;
@@ -343,10 +371,23 @@ static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
   return 0;
 }
 
+// PDLP_TRACE_SETUP=1: wall-clock of the setup stages on stderr (developer aid)
+struct SetupTrace {
+  bool on = getenv("PDLP_TRACE_SETUP") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pdlp setup] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 template <typename T>
 static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nnz, const int32_t* rowptr,
                       const int32_t* colidx, const void* vals) {
   cudaStream_t st = E->base->stream;
+  SetupTrace tr;
   A.rows = rows;
   A.cols = cols;
   A.nnz = nnz;
@@ -362,9 +403,11 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   if (h_rowptr[0] != 0 || h_rowptr[rows] != nnz) return fail(PDLP_ERR_INVALID, "rowptr does not span [0, nnz]");
   for (int r = 0; r < rows; ++r)
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
+  tr.lap("csr copy + rowptr to host");
   using Cfg = StreamCfg<T>;
   HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW,
                                E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
+  tr.lap("plan (host)");
   // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows
   A.stage_bytes = (P.max_piece_bytes + 127) / 128 * 128;
   A.nstages = std::max(2, std::min(Cfg::SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)Cfg::W * A.stage_bytes))));
@@ -390,6 +433,7 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   int rc = repack<T>(E, A);
   if (rc) return rc;
   CU(cudaStreamSynchronize(st));
+  tr.lap("alloc + plan upload + pack");
   return 0;
 }
 
@@ -407,6 +451,7 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   B->impl = E;
   const int m = (int)B->m, n = (int)B->n, nnz = (int)B->nnz;
   cudaStream_t st = B->stream;
+  SetupTrace tr;
   // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
   int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals);
   if (rc) return rc;
@@ -447,6 +492,7 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   h.m_ineq = (int)B->m_ineq;
   CU(cudaMemcpyAsync(E->S, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
+  tr.lap("engine_create total");
   return 0;
 }
 
@@ -735,6 +781,8 @@ static int engine_power_iteration(EngineT<T>* E, const void* b0, int iters, doub
   T* v = E->tmp_n2;
   T* w = E->tmp_m;
   CU(cudaMemcpyAsync(b, b0, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
+  // (folding b = v / ||v|| into the next pass's gather was measured: the fp64 division per gathered element makes
+  // the iteration slower, 110 vs 88 us, so the normalisation stays a separate streaming kernel)
   for (int i = 0; i < iters; ++i) {
     SpmvOp<T, false> f{b, w, E->S, 2};
     CU(launch_stream(E->K, f, st));
