@@ -49,13 +49,17 @@ struct HostSell {
 };
 
 static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int value_bytes, int W, int KB, int sigma,
-                                int long_row, int max_grid) {
+                                int long_row, int warp_row, int max_grid) {
   HostSell P;
   auto len = [&](int r) { return rowptr[r + 1] - rowptr[r]; };
-  std::vector<int> order;
+  // three classes of rows: one per lane (SELL slices), one per warp (32 equal segments, one per lane: the heavy
+  // tail of a power-law matrix would otherwise pad its slice mates and make single slices larger than a warp's
+  // share of the matrix), one per CTA (the few giants, straight from CSR)
+  std::vector<int> order, warp_rows;
   order.reserve(rows);
   for (int r = 0; r < rows; ++r) {
     if (len(r) > long_row) P.long_rows.push_back(r);
+    else if (len(r) > warp_row) warp_rows.push_back(r);
     else order.push_back(r);
   }
   // Sort by length (descending, stable) inside windows of sigma rows: neighbours in a slice get equal lengths.
@@ -113,28 +117,32 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     for (int r : tmp) order[w0 + (size_t)hist[(size_t)(len(r) - lo)]++] = r;
   }
   while (order.size() % 32) order.push_back(-1);
+  const int nsl_lane = (int)(order.size() / 32);
+  for (int r : warp_rows) order.insert(order.end(), 32, r);       // a warp-row slice: the same row in all 32 lanes
   P.perm = order;
   const int nsl = (int)(order.size() / 32);
   std::vector<int> klen(nsl, 0);
-  for (int i = 0; i < nsl; ++i)
+  for (int i = 0; i < nsl_lane; ++i)
     for (int r = 0; r < 32; ++r) {
       const int row = order[(size_t)i * 32 + r];
       if (row >= 0) klen[i] = std::max(klen[i], len(row));
     }
+  for (int i = nsl_lane; i < nsl; ++i) klen[i] = (len(order[(size_t)i * 32]) + 31) / 32;
   std::vector<int> kbase;   // first step (position inside the row) covered by each piece
   const int MAXSL = 16;     // StreamCfg::MAXSL
   for (int i = 0; i < nsl;) {
-    if (klen[i] > KB) {
+    if (klen[i] > KB || i >= nsl_lane) {
+      const uint32_t wr = i >= nsl_lane ? PIECE_WARP_ROW : 0u;
       for (int k0 = 0; k0 < klen[i]; k0 += KB) {
         Piece pc{0, i * 32, (uint16_t)std::min(KB, klen[i] - k0), 1,
-                 (k0 == 0 ? PIECE_FIRST : 0u) | (k0 + KB >= klen[i] ? PIECE_LAST : 0u)};
+                 (k0 == 0 ? PIECE_FIRST : 0u) | (k0 + KB >= klen[i] ? PIECE_LAST : 0u) | wr};
         P.pieces.push_back(pc);
         kbase.push_back(k0);
       }
       ++i;
     } else {
       int j = i, kmax = klen[i];
-      while (j + 1 < nsl && (j + 1 - i) < MAXSL && klen[j + 1] <= KB &&
+      while (j + 1 < nsl_lane && (j + 1 - i) < MAXSL && klen[j + 1] <= KB &&
              std::max(kmax, klen[j + 1]) * (j + 2 - i) <= KB) {
         kmax = std::max(kmax, klen[j + 1]);
         ++j;
@@ -210,7 +218,12 @@ __global__ void pack_kernel(const Piece* pieces, const int* perm, int npieces, c
       int src = -1;
       if (row >= 0) {
         const int b = rowptr[row], e = rowptr[row + 1];
-        if (b + kbase + k < e) src = b + kbase + k;
+        if (pc.flags & PIECE_WARP_ROW) {          // lane r owns entries [r * seg, (r + 1) * seg) of the row
+          const int seg = (e - b + 31) / 32;
+          if (kbase + k < seg && b + r * seg + kbase + k < e) src = b + r * seg + kbase + k;
+        } else if (b + kbase + k < e) {
+          src = b + kbase + k;
+        }
       }
       cdst[i] = src >= 0 ? colidx[src] : 0;
       vdst[i] = src >= 0 ? vals[src] : T(0);
@@ -405,7 +418,7 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   tr.lap("csr copy + rowptr to host");
   using Cfg = StreamCfg<T>;
-  HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW,
+  HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
                                E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
   tr.lap("plan (host)");
   // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows

@@ -50,7 +50,10 @@ namespace pdlp {
 #define PDLP_SIGMA 1024   // sorting window (rows)
 #endif
 #ifndef PDLP_LONG_ROW
-#define PDLP_LONG_ROW 1024
+#define PDLP_LONG_ROW 8192   // rows above this: one row per CTA, straight from CSR
+#endif
+#ifndef PDLP_WARP_ROW
+#define PDLP_WARP_ROW 256    // rows above this (up to PDLP_LONG_ROW): one row per WARP, 32 equal segments, one per lane
 #endif
 
 struct Piece {            // 16 bytes
@@ -58,10 +61,10 @@ struct Piece {            // 16 bytes
   int32_t perm_off;       // index into perm[] of the piece's first slice
   uint16_t klen;          // steps per slice inside this piece
   uint16_t nslices;       // slices in this piece (1 for a piece of a long slice)
-  uint32_t flags;         // PIECE_FIRST: rows start here; PIECE_LAST: rows end here
-};
+  uint32_t flags;         // PIECE_FIRST: rows start here; PIECE_LAST: rows end here; PIECE_WARP_ROW: the 32 lanes
+};                        // hold 32 segments of ONE row (their sums are combined before the row epilogue)
 static_assert(sizeof(Piece) == 16, "Piece must be 16 bytes");
-constexpr uint32_t PIECE_FIRST = 1u, PIECE_LAST = 2u;
+constexpr uint32_t PIECE_FIRST = 1u, PIECE_LAST = 2u, PIECE_WARP_ROW = 4u;
 
 constexpr int MAX_RED = 24;
 
@@ -347,7 +350,16 @@ __device__ __forceinline__ void stream_phase(const SellView<typename Op::value_t
           if (k0 + j < klen) op.mac(acc, vals[(bse + k0 + j) * 32 + lane], g[j]);
       }
 #ifndef PDLP_DBG_NOEPI
-      if ((d.flags & PIECE_LAST) && row >= 0) op.row_finish(row, ctx, acc, red);
+      if (d.flags & PIECE_WARP_ROW) {           // warp-uniform: a medium-long row spread over the 32 lanes
+        if (d.flags & PIECE_LAST) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
+          }
+          if (lane == 0) op.row_finish(row, ctx, acc, red);
+        }
+      } else if ((d.flags & PIECE_LAST) && row >= 0) op.row_finish(row, ctx, acc, red);
 #else
       if ((d.flags & PIECE_LAST) && row >= 0) red[0] += (double)acc[0];
 #endif
