@@ -63,9 +63,8 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     else order.push_back(r);
   }
   // Sort by length (descending, stable) inside windows of sigma rows: neighbours in a slice get equal lengths.
-  // sigma is adaptive: the smallest window (starting from the requested one) whose padded size stays within 5 % of
-  // the nonzeros -- heavy-tailed row lengths need a wide window (config 4: 1.74x padding at 1024 rows, 1.05x at
-  // 16384), uniform ones keep the narrow window and with it the locality of the row epilogue.
+  // sigma is chosen per matrix by a cost model (below): heavy-tailed row lengths need a wide window to avoid padding,
+  // near-uniform ones keep a narrow window and with it the locality of the row epilogue.
   // (lengths are small integers, <= long_row: histograms and a stable counting sort instead of comparison sorts --
   // the planner is on the end-to-end path of every solve)
   std::vector<int> hist, tmp;
@@ -81,11 +80,16 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     for (size_t i = w0; i < w1; ++i) ++hist[(size_t)(len(order[i]) - lo)];
   };
   {
-    long long nnz_short = 0;
-    for (int r : order) nnz_short += len(r);
+    // sigma minimises  padded slots x (index + value bytes)  +  rows x epilogue sector bytes x g(sigma):
+    // a wide window removes padding, a narrow one keeps the rows of a slice (and of the next slices of the same
+    // warp) within a few cache lines, so that the scattered epilogue accesses share sectors in L1.  g is the
+    // measured share of epilogue accesses that fetch their own 32-byte sector from L2 (configs 2 and 4, K and K^T:
+    // sigma = 128 / 256 / 1024 -> 36.7 / 39.1 / 41.2 us for K1 of config 2, 282 / 293 / 363 us for K1 of config 4).
+    auto g = [](int cand) { return cand <= 128 ? 0.25 : cand <= 256 ? 0.35 : cand <= 512 ? 0.6 : 1.0; };
+    const double epi_bytes = 6 * 32.0;
+    double best_cost = 0.0;
     int best = sigma;
-    for (int cand = sigma; cand <= (1 << 18); cand *= 4) {
-      best = cand;
+    for (int cand = sigma; cand <= (1 << 18); cand = cand < 1024 ? cand * 2 : cand * 4) {
       long long padded = 0;
       for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)cand) {
         const size_t w1 = std::min(order.size(), w0 + (size_t)cand);
@@ -99,9 +103,15 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
           placed += cnt;
         }
       }
-      if (padded <= nnz_short + nnz_short / 20 || (size_t)cand >= order.size()) break;
+      const double cost = (double)padded * (4 + value_bytes) + (double)order.size() * epi_bytes * g(cand);
+      if (cand == sigma || cost < best_cost) {
+        best_cost = cost;
+        best = cand;
+      }
+      if ((size_t)cand >= order.size()) break;
     }
     sigma = best;
+    if (getenv("PDLP_TRACE_SETUP")) fprintf(stderr, "[pdlp setup] sorting window %d rows\n", sigma);
   }
   for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {     // stable, descending by length
     const size_t w1 = std::min(order.size(), w0 + (size_t)sigma);

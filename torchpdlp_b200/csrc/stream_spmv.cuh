@@ -47,7 +47,7 @@ namespace pdlp {
 #define PDLP_MINB 1       // CTAs per SM the register budget is sized for
 #endif
 #ifndef PDLP_SIGMA
-#define PDLP_SIGMA 1024   // sorting window (rows)
+#define PDLP_SIGMA 128    // smallest sorting window (rows) the planner considers
 #endif
 #ifndef PDLP_LONG_ROW
 #define PDLP_LONG_ROW 8192   // rows above this: one row per CTA, straight from CSR
