@@ -89,6 +89,8 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     const double epi_bytes = 6 * 32.0;
     double best_cost = 0.0;
     int best = sigma;
+    long long nnz_short = 0;
+    for (int r : order) nnz_short += len(r);
     for (int cand = sigma; cand <= (1 << 18); cand = cand < 1024 ? cand * 2 : cand * 4) {
       long long padded = 0;
       for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)cand) {
@@ -109,6 +111,9 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
         best = cand;
       }
       if ((size_t)cand >= order.size()) break;
+      // no wider window can win once even zero padding would not pay for its worse locality
+      const int next = cand < 1024 ? cand * 2 : cand * 4;
+      if ((double)nnz_short * (4 + value_bytes) + (double)order.size() * epi_bytes * g(next) >= best_cost) break;
     }
     sigma = best;
     if (getenv("PDLP_TRACE_SETUP")) fprintf(stderr, "[pdlp setup] sorting window %d rows\n", sigma);

@@ -7,6 +7,8 @@ host read-back per restart check.
 """
 from __future__ import annotations
 
+import os
+import sys
 import time
 
 import torch
@@ -125,12 +127,21 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
     arguments (power_iters, b0, use_graph, return_info) have reference-compatible
     defaults."""
     t_start = time.time()
+    trace_t = [] if os.environ.get("PDLP_TRACE_SETUP") else None
+
+    def lap(what):
+        if trace_t is not None:
+            torch.cuda.synchronize()
+            trace_t.append((what, time.time()))
+
     engine = _cache.engine_for(K, m_ineq, c, q, l, u, device)
+    lap("engine_for")
     scaled = bool(precondition)
     if precondition and data_precond is not None:
         D_col, D_row = data_precond[0], data_precond[1]
         engine.set_scaling(D_row, D_col)
     eta, omega, sigma = initial_step(engine, power_iters, b0)
+    lap("initial_step")
     if x_init is not None and y_init is not None:                          # :31-33
         engine.set_iterate(x_init, y_init)
     else:
@@ -147,9 +158,15 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
         out = engine.solve(max_kkt, restart_period, time_limit, time_used + (time.time() - t_start), use_graph)
         prim_obj, k, n, j, status, trace = out.prim_obj, out.k, out.n, out.j, out.status, out.trace
         device_ms = out.device_ms
+    lap("solve")
     x, y = engine.get_iterate()
     torch.cuda.synchronize(engine.device)
     total = time.time() - t_start + time_used
+    if trace_t is not None:
+        prev = t_start
+        for what, t in trace_t:
+            print(f"[pdlp host] {what:14s} {1e3 * (t - prev):8.2f} ms", file=sys.stderr)
+            prev = t
     if return_info:
         info = {"y": y.reshape(-1, 1), "trace": trace, "sigma_max": sigma, "engine": engine, "device_ms": device_ms,
                 "bytes_per_iteration": engine.bytes_per_iteration}
