@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <mutex>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -292,6 +293,28 @@ struct pdlp_engine {
 
 static void xchg_release(pdlp_engine* B);
 
+// pinned read-back buffers are recycled across engines: cudaMallocHost / cudaFreeHost are synchronous and cost
+// milliseconds with a large variance, which would sit on the end-to-end path of every solve
+static std::mutex g_pinned_mutex;
+static std::vector<void*> g_pinned_free;
+static void* pinned_scalars_get() {
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_free.empty()) {
+      void* p = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, sizeof(Scalars)) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_scalars_put(void* p) {
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_pinned_free.push_back(p);
+}
+
 template <typename T>
 struct EngineT {
   pdlp_engine* base;
@@ -495,7 +518,8 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
   ALLOC(E->S, 1);
   E->ew_grid = B->sms * 2;
-  CU(cudaMallocHost((void**)&E->h_scalars, sizeof(Scalars)));
+  E->h_scalars = (Scalars*)pinned_scalars_get();
+  if (!E->h_scalars) return fail(PDLP_ERR_CUDA, "cudaMallocHost failed");
   ALLOC(E->ew_partials, 2 * E->ew_grid);
   ALLOC(E->kkt_partials, 16 * E->ew_grid);
   ALLOC(E->blk_partP, 2 * B->sms * 4);
@@ -532,7 +556,7 @@ static void engine_destroy(pdlp_engine* B) {
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b)
       if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
-  if (E->h_scalars) cudaFreeHost(E->h_scalars);
+  if (E->h_scalars) pinned_scalars_put(E->h_scalars);
   xchg_release(B);
   for (void* p : E->allocs) cudaFreeAsync(p, B->stream);
   cudaStreamSynchronize(B->stream);
