@@ -111,6 +111,28 @@ const char* pdlp_last_error(void);
  * (SURVEY.md section 8d).  For reporting only. */
 int64_t pdlp_bytes_per_iteration(pdlp_handle h);
 
+/* Host-only inspection of the layout the planner would build for a matrix with these row lengths (no device
+ * work, usable without a GPU: the `-m "not gpu"` tests check its invariants).  value_bytes = 8 or 4; sms = number
+ * of SMs to plan for (148 on B200).  host_row_class (may be NULL) receives per row 0 = lane row (SELL slice),
+ * 1 = warp row (32 segments of one row), 2 = CTA row (straight from CSR).                                       */
+typedef struct pdlp_plan_info {
+  int64_t rows, nnz;
+  int64_t lane_rows, warp_rows, cta_rows;
+  int64_t slots;        /* padded (index, value) slots of the packed copy; >= nnz - nnz of the CTA rows */
+  int64_t packed_bytes; /* headers + row ids + slots */
+  int32_t sigma;        /* sorting window chosen by the cost model */
+  int32_t grid;         /* CTAs */
+  int32_t warps;        /* grid x warps per CTA */
+  int32_t pieces;
+  int32_t max_piece_bytes;
+  int32_t stages;       /* ring stages per warp */
+  int64_t max_warp_bytes, mean_warp_bytes; /* balance of the per-warp piece ranges */
+  int32_t covered_once; /* 1 iff every row appears in exactly one class and every lane row in exactly one slice lane */
+  int32_t ranges_ok;    /* 1 iff the warp ranges are monotone, cover all pieces and start where rows start */
+} pdlp_plan_info;
+int pdlp_plan_inspect(const int32_t* host_rowptr, int64_t rows, int32_t value_bytes, int32_t sms,
+                      pdlp_plan_info* host_out, int8_t* host_row_class);
+
 /* ---- lifetime -------------------------------------------------------------
  * Problem tuple (c, K, q, m_ineq, l, u): reference PDLP/util.py:239-269,
  * consumed at primal_dual_hybrid_gradient.py:7.  K is given as CSR (m x n) AND

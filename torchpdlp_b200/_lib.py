@@ -53,6 +53,14 @@ class SolveResult(C.Structure):
 
 
 # every symbol include/pdlp_b200.h declares: name -> (restype, argtypes)
+class PlanInfo(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("nnz", C.c_int64), ("lane_rows", C.c_int64), ("warp_rows", C.c_int64),
+                ("cta_rows", C.c_int64), ("slots", C.c_int64), ("packed_bytes", C.c_int64), ("sigma", C.c_int32),
+                ("grid", C.c_int32), ("warps", C.c_int32), ("pieces", C.c_int32), ("max_piece_bytes", C.c_int32),
+                ("stages", C.c_int32), ("max_warp_bytes", C.c_int64), ("mean_warp_bytes", C.c_int64),
+                ("covered_once", C.c_int32), ("ranges_ok", C.c_int32)]
+
+
 _P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SYMBOLS = {
     "pdlp_last_error": (C.c_char_p, []),
@@ -83,6 +91,7 @@ SYMBOLS = {
     "pdlp_batch_spmv": (_I, [_P, _P, _P]),
     "pdlp_batch_step": (_I, [_P, _P, _P, _P, _D, _D]),
     "pdlp_batch_gap": (_I, [_P, _P, _P, C.POINTER(_D)]),
+    "pdlp_plan_inspect": (_I, [_P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(PlanInfo), _P]),
     "pdlp_shard_enable": (_I, [_P, _D, _D]),
     "pdlp_shard_kty": (_I, [_P, _P]),
     "pdlp_shard_step": (_I, [_P, _P, _I]),

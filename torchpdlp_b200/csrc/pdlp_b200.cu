@@ -47,6 +47,7 @@ struct HostSell {
   size_t packed_bytes = 0;
   int grid = 1;
   int max_piece_bytes = 16;
+  int sigma = 0;                       // sorting window the cost model chose
 };
 
 static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int value_bytes, int W, int KB, int sigma,
@@ -117,6 +118,7 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
       if ((double)nnz_short * (4 + value_bytes) + (double)order.size() * epi_bytes * g(next) >= best_cost) break;
     }
     sigma = best;
+    P.sigma = sigma;
     if (getenv("PDLP_TRACE_SETUP")) fprintf(stderr, "[pdlp setup] sorting window %d rows\n", sigma);
   }
   for (size_t w0 = 0; w0 < order.size(); w0 += (size_t)sigma) {     // stable, descending by length
@@ -1368,6 +1370,79 @@ extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, in
     return rc;
   }
   *out = B;
+  return 0;
+}
+
+extern "C" int pdlp_plan_inspect(const int32_t* host_rowptr, int64_t rows, int32_t value_bytes, int32_t sms,
+                                 pdlp_plan_info* o, int8_t* row_class) {
+  if (!host_rowptr || !o || rows < 0 || rows > 0x7fffffff || (value_bytes != 4 && value_bytes != 8) || sms < 1)
+    return fail(PDLP_ERR_INVALID, "bad argument");
+  std::vector<int> rowptr(host_rowptr, host_rowptr + rows + 1);
+  for (int64_t r = 0; r < rows; ++r)
+    if (rowptr[r + 1] < rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
+  const int W = PDLP_W, KB = PDLP_KB;
+  HostSell P = build_sell_plan(rowptr, (int)rows, value_bytes, W, KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
+                               sms * PDLP_CTAS * PDLP_OVERSUB);
+  memset(o, 0, sizeof(*o));
+  o->rows = rows;
+  o->nnz = rowptr[rows] - rowptr[0];
+  o->cta_rows = (int64_t)P.long_rows.size();
+  o->sigma = P.sigma;
+  o->grid = P.grid;
+  o->warps = P.grid * W;
+  o->pieces = (int32_t)P.pieces.size();
+  o->max_piece_bytes = P.max_piece_bytes;
+  o->packed_bytes = (int64_t)P.packed_bytes;
+  const int stage = (P.max_piece_bytes + 127) / 128 * 128;
+  o->stages = std::max(2, std::min((int)PDLP_SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)W * stage))));
+  // classes and coverage
+  std::vector<int> seen(rows, 0);
+  std::vector<int8_t> cls(rows, -1);
+  bool ok = true;
+  for (int r : P.long_rows) {
+    if (r < 0 || r >= rows) { ok = false; continue; }
+    ++seen[r];
+    cls[r] = 2;
+  }
+  for (const Piece& pc : P.pieces) {
+    o->slots += (int64_t)pc.klen * pc.nslices * 32;
+    if (!(pc.flags & PIECE_FIRST)) continue;
+    for (int i = 0; i < (int)pc.nslices * 32; ++i) {
+      const int r = P.perm[(size_t)pc.perm_off + i];
+      if (r < 0) continue;
+      if (r >= rows) { ok = false; continue; }
+      if (pc.flags & PIECE_WARP_ROW) {
+        if (i == 0) { ++seen[r]; cls[r] = 1; }
+        else if (r != P.perm[(size_t)pc.perm_off]) ok = false;
+      } else {
+        ++seen[r];
+        cls[r] = 0;
+      }
+    }
+  }
+  for (int64_t r = 0; r < rows; ++r) {
+    if (seen[r] != 1) ok = false;
+    if (cls[r] == 0) ++o->lane_rows;
+    if (cls[r] == 1) ++o->warp_rows;
+    if (row_class) row_class[r] = cls[r];
+  }
+  o->covered_once = ok ? 1 : 0;
+  // warp ranges
+  bool rok = (int)P.warp_begin.size() == o->warps + 1 && P.warp_begin.front() == 0 && P.warp_begin.back() == o->pieces;
+  int64_t maxb = 0, sumb = 0;
+  for (int w = 0; rok && w < o->warps; ++w) {
+    const int b = P.warp_begin[w], e = P.warp_begin[w + 1];
+    if (b > e) { rok = false; break; }
+    if (b < e && !(P.pieces[b].flags & PIECE_FIRST)) rok = false;
+    int64_t bytes = 0;
+    for (int p = b; p < e; ++p) bytes += 16 + ((P.pieces[p].flags & PIECE_FIRST) ? (int64_t)P.pieces[p].nslices * 128 : 0) +
+                                         (int64_t)P.pieces[p].klen * P.pieces[p].nslices * 32 * (4 + value_bytes);
+    maxb = std::max(maxb, bytes);
+    sumb += bytes;
+  }
+  o->ranges_ok = rok ? 1 : 0;
+  o->max_warp_bytes = maxb;
+  o->mean_warp_bytes = o->warps ? sumb / o->warps : 0;
   return 0;
 }
 
