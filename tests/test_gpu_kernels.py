@@ -25,14 +25,18 @@ def oracle_parts(lp):
 
 
 def ragged_lp(seed=3):
-    """Rows of every kind in one matrix: empty rows, 1-entry rows, a 5000-entry row
-    (longer than one shared-memory stage -> the long-row path), dense-ish blocks."""
+    """Rows of every kind in one matrix: empty rows, 1-entry rows, lane rows up to the 256-entry limit, warp rows
+    (257, 2300 and 5000 entries: 32 segments of one row, several pieces) and a 12000-entry CTA row (straight from
+    CSR), see stream_spmv.cuh."""
     rng = np.random.default_rng(seed)
-    m, n = 700, 6000
+    m, n = 700, 20000
     lens = rng.integers(0, 40, size=m)
     lens[::17] = 0
     lens[5] = 5000
     lens[300] = 2300
+    lens[301] = 257
+    lens[302] = 256
+    lens[400] = 12000
     lens[699] = 1
     rows = np.repeat(np.arange(m), lens)
     cols = np.concatenate([np.sort(rng.choice(n, size=L, replace=False)) for L in lens]) if lens.sum() else np.array([])
@@ -59,6 +63,24 @@ def test_spmv_both_directions(which, cfg1):
     got_t = eng.spmv(w, transpose=True).cpu().numpy()
     ref_t = lp.K.T @ w
     assert np.max(np.abs(got_t - ref_t)) <= 1e-12 * max(1.0, np.max(np.abs(ref_t)))
+    eng.close()
+
+
+def test_spmv_fp32_ragged():
+    """The fp32 instantiation on every row class (piece sizes differ from fp64: 8 instead of 12 bytes per slot)."""
+    lp = ragged_lp()
+    eng = make_engine(lp, dtype=torch.float32)
+    rng = np.random.default_rng(1)
+    v, w = rng.normal(size=lp.n).astype(np.float32), rng.normal(size=lp.m).astype(np.float32)
+    K32 = lp.K.astype(np.float32)
+    got = eng.spmv(torch.from_numpy(v)).cpu().numpy()
+    ref = lp.K @ v.astype(np.float64)
+    scale = np.abs(K32) @ np.abs(v)                              # fp32 rounding grows with the row's magnitude sum
+    assert np.all(np.abs(got - ref) <= 4e-6 * np.maximum(scale, 1.0))
+    got_t = eng.spmv(torch.from_numpy(w), transpose=True).cpu().numpy()
+    ref_t = lp.K.T @ w.astype(np.float64)
+    scale_t = np.abs(K32).T @ np.abs(w)
+    assert np.all(np.abs(got_t - ref_t) <= 4e-6 * np.maximum(scale_t, 1.0))
     eng.close()
 
 
