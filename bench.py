@@ -365,7 +365,7 @@ def run_sharded(args, world, rank, local, dev):
 
     def note(msg):
         if os.environ.get("PDLP_BENCH_TRACE"):
-            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+            print(f"[rank {rank} t={time.perf_counter():.3f}] {msg}", file=sys.stderr, flush=True)
 
     reset()
     note("warmup")

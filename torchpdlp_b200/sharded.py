@@ -20,6 +20,8 @@ points so the orchestration below can be exercised on CPU with a test double
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import time
 from typing import Optional, Tuple
 
@@ -178,8 +180,11 @@ class ShardedSolver:
         self.q_norm, self.c_norm = float(t.item()) ** 0.5, c_norm
         prims.enable(self.q_norm, self.c_norm)
         if exchange == "p2p":
+            t_x = time.time()
             prims.exchange_connect(group)
             self._p2p_ready = True
+            if os.environ.get("PDLP_TRACE_SETUP"):
+                print(f"[pdlp host] exchange_connect      {1e3 * (time.time() - t_x):8.2f} ms", file=sys.stderr, flush=True)
 
     def _allreduce(self, t):
         if self._p2p_ready and t.dtype == torch.float64 and t.is_contiguous():
@@ -233,7 +238,10 @@ class ShardedSolver:
             return self._iterate_eager(n_iters, save_previous)
         if state == "warm":
             before = self.collectives
+            t_cap = time.time()
             state = self.p.capture_block(lambda: self._iterate_eager(n_iters, save_previous))
+            if os.environ.get("PDLP_TRACE_SETUP"):
+                print(f"[pdlp host] sharded graph capture {1e3 * (time.time() - t_cap):8.2f} ms", file=sys.stderr, flush=True)
             self.collectives = before
             self._graphs[key] = state
         state()
@@ -274,6 +282,9 @@ class ShardedSolver:
         from .primal_dual_hybrid_gradient import run_restart_loop
         t0 = time.time()
         eta, omega, sigma = self.initial_step(power_iters, b0)
+        if os.environ.get("PDLP_TRACE_SETUP"):
+            self.p.sync()
+            print(f"[pdlp host] sharded initial_step {1e3 * (time.time() - t0):8.2f} ms", file=sys.stderr, flush=True)
         self.p.set_iterate(x_init, y_init_local)
         self.p.set_counters(0, 0)
         self.p.set_step(eta, omega, 1.0, adaptive)
@@ -283,6 +294,9 @@ class ShardedSolver:
         prim_obj, k, n, j, status, trace = run_restart_loop(self, max_kkt, restart_period, time_limit, 0.0,
                                                             verbose and rank0, False, use_graph=use_graph, t_start=t0)
         x, y_local = self.p.get_iterate()
+        if os.environ.get("PDLP_TRACE_SETUP"):
+            self.p.sync()
+            print(f"[pdlp host] sharded solve total  {1e3 * (time.time() - t0):8.2f} ms (k={k})", file=sys.stderr, flush=True)
         return x, y_local, prim_obj, k, n, j, status, time.time() - t0, sigma
 
 
