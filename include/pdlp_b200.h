@@ -270,11 +270,14 @@ int pdlp_shard_check_end(pdlp_handle h, const double* buf1, pdlp_check* host_out
  *                                update as the sums arrive; the local dual kernel.  Capturable in a CUDA graph.
  *   pdlp_shard_allreduce_p2p     in-place sum of `count` device doubles over the same block (the small collectives
  *                                of the restart test and of the power iteration)
+ *   pdlp_shard_exchange_disconnect  unmaps the peers' blocks; call it on every rank, then a host barrier, before
+ *                                pdlp_destroy frees the rank's own block
  * Every rank must enqueue the same calls in the same order; a rank that waits > 20 s for a peer stops and the next
  * pdlp_shard_check_end reports the error.                                                             */
 #define PDLP_IPC_HANDLE_BYTES 64
 int pdlp_shard_exchange_create(pdlp_handle h, int world, int rank, unsigned char* handle_out);
 int pdlp_shard_exchange_connect(pdlp_handle h, const unsigned char* handles);
+int pdlp_shard_exchange_disconnect(pdlp_handle h);
 int pdlp_shard_iterate_p2p(pdlp_handle h, int n_iters, int save_previous);
 int pdlp_shard_allreduce_p2p(pdlp_handle h, double* buf, int64_t count);
 

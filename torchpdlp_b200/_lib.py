@@ -103,6 +103,7 @@ SYMBOLS = {
     "pdlp_shard_check_end": (_I, [_P, _P, C.POINTER(Check)]),
     "pdlp_shard_exchange_create": (_I, [_P, _I, _I, _P]),
     "pdlp_shard_exchange_connect": (_I, [_P, _P]),
+    "pdlp_shard_exchange_disconnect": (_I, [_P]),
     "pdlp_shard_iterate_p2p": (_I, [_P, _I, _I]),
     "pdlp_shard_allreduce_p2p": (_I, [_P, _P, C.c_int64]),
     "pdlp_solve": (_I, [_P, C.POINTER(SolveOptions), C.POINTER(SolveResult), C.POINTER(Check)]),

@@ -1031,12 +1031,19 @@ static size_t xchg_block_bytes(int L, int world) {
   return sizeof(double) * (size_t)L + 16 * ((size_t)world * xchg_seg(L, world) + (size_t)L);
 }
 
-static void xchg_release(pdlp_engine* B) {
+// unmap the peers' blocks (every rank does this, then a host barrier, before any rank frees its own block)
+static void xchg_disconnect(pdlp_engine* B) {
   for (int p = 0; p < MAX_PEERS; ++p)
     if (B->xchg_peer[p]) {
       cudaIpcCloseMemHandle(B->xchg_peer[p]);
       B->xchg_peer[p] = nullptr;
     }
+  B->xchg_connected = false;
+  cudaGetLastError();
+}
+
+static void xchg_release(pdlp_engine* B) {
+  xchg_disconnect(B);
   if (B->xchg_dev) cudaFree(B->xchg_dev);
   if (B->xchg_block) cudaFree(B->xchg_block);
   B->xchg_dev = nullptr;
@@ -1723,6 +1730,13 @@ extern "C" int pdlp_shard_exchange_connect(pdlp_handle h, const unsigned char* h
   if (!handles) return fail(PDLP_ERR_INVALID, "null argument");
   cudaSetDevice(h->device);
   return DISPATCH(h, xchg_connect, handles);
+}
+extern "C" int pdlp_shard_exchange_disconnect(pdlp_handle h) {
+  CHECK_HANDLE(h);
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  xchg_disconnect(h);
+  return 0;
 }
 extern "C" int pdlp_shard_iterate_p2p(pdlp_handle h, int n_iters, int save_previous) {
   CHECK_HANDLE(h);

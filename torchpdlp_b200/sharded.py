@@ -131,6 +131,9 @@ class GpuShardPrims:
         if world > 1:
             dist.barrier(group=group)              # every rank has mapped every block before the first flag is raised
 
+    def exchange_disconnect(self):
+        check(self.lib.pdlp_shard_exchange_disconnect(self.h))
+
     def allreduce_p2p(self, t):
         check(self.lib.pdlp_shard_allreduce_p2p(self.h, t.data_ptr(), t.numel()))
 
@@ -270,6 +273,12 @@ class ShardedSolver:
         self._graphs.clear()
         if hasattr(self.p, "e"):
             torch.cuda.synchronize(self.p.device)
+            if self._p2p_ready and self.p.e.h:
+                # every rank unmaps its peers before any rank frees its own exchange block
+                self.p.exchange_disconnect()
+                self._p2p_ready = False
+                if self.world > 1 and dist.is_initialized():
+                    dist.barrier(group=self.group)
             self.p.e.close()
 
     def primal_objective(self):
