@@ -128,6 +128,31 @@ class FakeShardPrims:
         self.y = yn
         s.dy2, s.inter, s.rule_pending = float(torch.dot(dy, dy)), float(torch.dot(dy, kdx)), 1
 
+    # ---- exchange="p2p": the same device work, the exchange done by the "kernels" (here: the process group) ----
+    def exchange_connect(self, group=None):
+        import torch.distributed as dist
+        self._group = group
+        self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.connected = True
+        self.p2p_exchanges = 0
+
+    def exchange_disconnect(self):
+        self.connected = False
+
+    def allreduce_p2p(self, t):
+        import torch.distributed as dist
+        assert self.connected
+        if self._world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
+        self.p2p_exchanges += 1
+
+    def iterate_p2p(self, n_iters, save_previous):
+        buf = self.buffer(self.n + 4)
+        for i in range(n_iters):
+            self.kty(buf)
+            self.allreduce_p2p(buf)
+            self.step(buf, save_previous and i == n_iters - 1)
+
     def rule_pack(self, buf4):
         buf4[0] = self.s.dy2 if self.s.rule_pending else 0.0
         buf4[1] = self.s.inter if self.s.rule_pending else 0.0

@@ -25,7 +25,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, adaptive, primal_update, out):
+def _worker(rank, world, port, adaptive, primal_update, out, exchange="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_default_dtype(torch.float64)
@@ -37,22 +37,27 @@ def _worker(rank, world, port, adaptive, primal_update, out):
     r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
     mi_local = min(max(lp.m_ineq - r0, 0), r1 - r0)
     prims = FakeShardPrims(lp.K[r0:r1], mi_local, lp.c, lp.q[r0:r1], lp.l, lp.u)
-    solver = ShardedSolver(prims)
+    solver = ShardedSolver(prims, exchange=exchange)
     torch.manual_seed(0)
     x, y_local, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=primal_update)
     ys = [torch.zeros(int(cuts[i + 1] - cuts[i])) for i in range(world)] if rank == 0 else None
     dist.gather(y_local, ys, dst=0)
     if rank == 0:
         out.put(dict(obj=obj, k=k, n=n, j=j, status=status, sigma=sigma, x=x.numpy(), y=torch.cat(ys).numpy(),
-                     collectives=solver.collectives, cuts=cuts.tolist()))
+                     collectives=solver.collectives, cuts=cuts.tolist(),
+                     p2p_exchanges=getattr(prims, "p2p_exchanges", None)))
+    solver.close()                       # p2p: unmap peers, barrier, then free -- every rank must get here
+    if exchange == "p2p":
+        assert not prims.connected
     dist.destroy_process_group()
 
 
-def run_world(world, adaptive, primal_update):
+def run_world(world, adaptive, primal_update, exchange="nccl"):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, adaptive, primal_update, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, adaptive, primal_update, out, exchange))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = out.get(timeout=600)
@@ -84,6 +89,18 @@ def test_two_rank_solve_matches_oracle(adaptive, primal_update):
     assert abs(res["sigma"] - sol.sigma_max) <= 1e-9 * sol.sigma_max
     # one exchange per iteration + 4 per restart test + setup (norm, 2 per power-iteration round + 1)
     assert res["collectives"] == res["k"] + 4 * (res["k"] // 40) + 1 + 100 + 1
+
+
+def test_two_rank_peer_exchange_orchestration():
+    """exchange="p2p": connect once, every collective of the solve (iterations, restart tests, power iteration)
+    goes through the peer-memory entry points, the teardown unmaps before it frees; same numbers as the
+    host-allreduce orchestration."""
+    a = run_world(2, True, True, "nccl")
+    b = run_world(2, True, True, "p2p")
+    assert (a["k"], a["n"], a["j"], a["status"]) == (b["k"], b["n"], b["j"], b["status"])
+    assert a["obj"] == b["obj"] and np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"])
+    # everything after the initial ||q|| norm (issued before the exchange is connected) is a peer-memory exchange
+    assert b["p2p_exchanges"] == b["collectives"] - 1 == b["k"] + 4 * (b["k"] // 40) + 100 + 1
 
 
 def test_partition_rows_balances_nnz():

@@ -271,14 +271,18 @@ class ShardedSolver:
     def close(self):
         """Drop the captured graphs (they hold NCCL work) and the engine; call before destroy_process_group."""
         self._graphs.clear()
-        if hasattr(self.p, "e"):
+        gpu = hasattr(self.p, "e")
+        if gpu:
+            if not self.p.e.h:
+                return
             torch.cuda.synchronize(self.p.device)
-            if self._p2p_ready and self.p.e.h:
-                # every rank unmaps its peers before any rank frees its own exchange block
-                self.p.exchange_disconnect()
-                self._p2p_ready = False
-                if self.world > 1 and dist.is_initialized():
-                    dist.barrier(group=self.group)
+        if self._p2p_ready:
+            # every rank unmaps its peers before any rank frees its own exchange block
+            self.p.exchange_disconnect()
+            self._p2p_ready = False
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)
+        if gpu:
             self.p.e.close()
 
     def primal_objective(self):
