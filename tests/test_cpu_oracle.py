@@ -62,6 +62,43 @@ def test_oracle_reproduces_executed_reference(idx, cfg1, gold):
     assert rel(sol.prim_obj, ref["obj"]) < (2e-6 if o["adaptive"] else 1e-9)
 
 
+with open(os.path.join(GOLD, "bounds_reference.json")) as _f:
+    BOUNDS_GOLD = json.load(_f)
+
+
+@pytest.mark.parametrize("run", BOUNDS_GOLD["runs"],
+                         ids=lambda r: "-".join(k for k, v in r["options"].items() if v) or "plain")
+def test_oracle_reproduces_reference_with_infinite_bounds(run):
+    """Box, lower-only, upper-only and free variables in one LP (synthetic.mixed_bounds_lp), the reference executed by
+    tests/golden/make_golden_bounds.py: the one-sided / free branches of the lambda projection and of the dual
+    objective, with and without Ruiz.  Fixed step: k / n / j / restart kinds equal, objective 1e-9.  Adaptive: the
+    runs are bitwise equal for ~800 iterations and then part by the rule's sensitivity (the reference's own dense and
+    COO runs do), so only verdict, optimum and the order of magnitude of k are compared."""
+    lp = synthetic.mixed_bounds_lp()
+    b = BOUNDS_GOLD["lp"]
+    assert (lp.m, lp.n, lp.nnz, lp.m_ineq) == (b["m"], b["n"], b["nnz"], b["m_ineq"])
+    assert int(np.sum(np.isinf(lp.l) & np.isinf(lp.u))) == b["bounds"]["free"] > 0
+    o, ref = run["options"], run["reference"]
+    sol = run_oracle(lp, o, layout="dense")
+    assert sol.status == ref["status"] == "Solved"
+    if o["adaptive"]:
+        assert 0.5 * ref["k"] <= sol.k <= 2 * ref["k"] and rel(sol.prim_obj, ref["obj"]) < 1e-4
+    else:
+        assert (sol.k, sol.n, sol.j) == (ref["k"], ref["n"], ref["j"])
+        assert [(r.kind, str(r.t), r.candidate) for r in sol.trace] == [tuple(r) for r in ref["restarts"]]
+        assert rel(sol.prim_obj, ref["obj"]) < 1e-9
+
+
+def test_torch_tensors_are_copies():
+    """The reference overwrites the infinite entries of the caller's l / u when precondition=True
+    (primal_dual_hybrid_gradient.py:157-158); tensors handed out by a SyntheticLP must not alias its arrays."""
+    lp = synthetic.mixed_bounds_lp()
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr")
+    l[torch.isinf(l)] = 0.0
+    u[torch.isinf(u)] = 0.0
+    assert np.isinf(lp.l).sum() > 0 and np.isinf(lp.u).sum() > 0
+
+
 def test_oracle_sparse_backends_agree(cfg1, gold):
     ref = gold["runs"][0]["reference"]
     for layout, backend in [("coo", "torch"), ("csr", "torch"), ("csr", "scipy")]:

@@ -65,6 +65,28 @@ def test_cfg1_against_executed_reference(run, cfg1):
     assert x.shape == (cfg1.n, 1) and x.is_cuda
 
 
+BOUNDS_RUNS = load("bounds_reference.json")["runs"]
+
+
+@pytest.mark.parametrize("run", BOUNDS_RUNS, ids=lambda r: "-".join(k for k, v in r["options"].items() if v) or "plain")
+def test_mixed_infinite_bounds_against_executed_reference(run):
+    """Box, lower-only, upper-only and free variables (synthetic.mixed_bounds_lp) against the executed reference:
+    fixed step exact in k / n / j and restart kinds, objective 1e-9; adaptive compared by verdict and optimum (the
+    reference's own runs part by a factor in k on this LP, tests/golden/make_golden_bounds.py)."""
+    lp = synthetic.mixed_bounds_lp()
+    o, ref = run["options"], run["reference"]
+    x, obj, k, n, j, status, secs, info = solve(lp, o["ruiz"], o["adaptive"], o["primal_weight"])
+    assert status == ref["status"] == "Solved"
+    if o["adaptive"]:
+        assert 0.5 * ref["k"] <= k <= 2 * ref["k"] and rel(obj, ref["obj"]) < 1e-4, (k, ref["k"], obj, ref["obj"])
+    else:
+        kinds = [(c.kind, c.use_average) for c in info["trace"]]
+        want = [({"Sufficient": 1, "Necessary": 2, "Artificial": 3}[a], 1 if c == "Average" else 0)
+                for a, _, c in ref["restarts"]]
+        assert (k, n, j) == (ref["k"], ref["n"], ref["j"]) and kinds == want
+        assert rel(obj, ref["obj"]) < 1e-9, (obj, ref["obj"])
+
+
 def test_cfg1_layouts_and_verbose_loop_agree(cfg1, capsys):
     """Dense, COO and CSR inputs and the verbose (host-driven) loop give the same solve
     as the C++ driver; the verbose lines have the reference's format (:132-170)."""

@@ -56,7 +56,9 @@ class SyntheticLP:
         import torch
         warnings.filterwarnings("ignore", message=".*Sparse (CSR|invariant).*")
         dtype = dtype or torch.float64
-        col = lambda v: torch.as_tensor(v, dtype=dtype).reshape(-1, 1).to(device)
+        # copies: the reference mutates its inputs (with precondition=True it overwrites the infinite entries of the
+        # caller's l and u, primal_dual_hybrid_gradient.py:157-158) and must not reach this LP's arrays through them
+        col = lambda v: torch.tensor(np.asarray(v), dtype=dtype).reshape(-1, 1).to(device)
         K = self.K
         if layout == "dense":
             Kt = torch.as_tensor(K.toarray(), dtype=dtype)
@@ -193,6 +195,25 @@ def powerlaw_rows_lp(m_ineq=1_600_000, m_eq=400_000, n=4_000_000, mean_nnz=25, a
     M = sp.csr_matrix((vals, cols.astype(np.int32), indptr), shape=(m, n))
     G, A = M[:m_ineq], M[m_ineq:]
     return _finish(name, G, A, x_feas, rng, m_ineq, m_eq, n)
+
+
+def mixed_bounds_lp(n=600, m_ineq=220, m_eq=60, density=0.03, seed=5, name="mixed_bounds"):
+    """Small feasible, bounded LP whose variables have all four kinds of bounds (box, lower only, upper only,
+    free): every 5th variable loses the bound its cost pushes away from (so the LP stays bounded), up to 20
+    variables (every 11th with at least 3 constraint entries) lose both and get cost 0.  Exercises the one-sided / free branches of the lambda projection
+    and of the dual objective (reference helpers.py:3-39, 70-112)."""
+    lp = feasible_lp(n, m_ineq, m_eq, density, seed, name)
+    l, u, c = lp.l.copy(), lp.u.copy(), lp.c.copy()
+    for j in range(0, n, 5):
+        if c[j] > 0:
+            u[j] = np.inf
+        else:
+            l[j] = -np.inf
+    # free variables: cost 0 (the objective cannot run away along them), present in at least 3 rows
+    col_nnz = np.diff(lp.K.tocsc().indptr)
+    for j in [j for j in range(3, n, 11) if col_nnz[j] >= 3][:20]:
+        l[j], u[j], c[j] = -np.inf, np.inf, 0.0
+    return SyntheticLP(name, lp.K, c, lp.q, l, u, lp.m_ineq)
 
 
 CONFIGS = {
