@@ -112,6 +112,21 @@ def test_cfg1_kkt_limit_and_warm_start(cfg1):
     assert st2 == "Solved" and k2 == 40 and rel(obj2, objs) < 1e-4
 
 
+def test_time_limit_status(cfg1):
+    """The reference tests the clock before every iteration (primal_dual_hybrid_gradient.py:68-74); the engine tests
+    it before every block of iterations.  A budget that is already spent returns at once with the reference's
+    status string and untouched counters; a budget that runs out mid-solve stops at a block boundary."""
+    x, obj, k, n, j, status, secs, info = solve(cfg1, time_limit=0.0)
+    assert status == "Unsolved (Time limit exceeded)" and (k, n, j) == (0, 0, 0)
+    assert torch.count_nonzero(x).item() == 0
+    lp = synthetic.make("cfg2")
+    for verbose in (False, True):       # fixed step: 2880 iterations (~0.18 s) to converge, the budget ends earlier
+        x, obj, k, n, j, status, secs, info = solve(lp, time_limit=0.1, verbose=verbose, power_iters=5)
+        assert status == "Unsolved (Time limit exceeded)"
+        assert k < 2880 and k % 40 == 0 and secs >= 0.1
+        assert k == 0 or np.isfinite(obj)
+
+
 @pytest.mark.parametrize("idx", [0, 1])
 def test_cfg2_full_size_against_oracle(idx):
     gold = load("cfg2_oracle.json")
