@@ -114,11 +114,29 @@ class GpuShardPrims:
     IPC_HANDLE_BYTES = 64
 
     def exchange_connect(self, group=None):
-        """Allocate this rank's exchange block, all-gather the CUDA IPC handles and map the peers' blocks."""
+        """Allocate this rank's exchange block, all-gather the CUDA IPC handles and map the peers' blocks.  A failure
+        on any rank (e.g. CUDA IPC not permitted) is agreed on collectively and raised on EVERY rank, so the
+        callers' collectives stay matched."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+        def agree(err):
+            if world > 1:
+                bad = torch.tensor([0.0 if err is None else 1.0], device=self.device)
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+                if float(bad.item()) > 0:
+                    raise RuntimeError(f"peer-memory exchange unavailable on rank {rank}: {err}" if err is not None
+                                       else "peer-memory exchange unavailable on another rank")
+            elif err is not None:
+                raise err
+
         mine = (C.c_ubyte * self.IPC_HANDLE_BYTES)()
-        check(self.lib.pdlp_shard_exchange_create(self.h, world, rank, C.cast(mine, C.c_void_p)))
+        err = None
+        try:
+            check(self.lib.pdlp_shard_exchange_create(self.h, world, rank, C.cast(mine, C.c_void_p)))
+        except Exception as exc:                       # noqa: BLE001 -- reported to every rank below
+            err = exc
+        agree(err)
         t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
         if world > 1:
             every = torch.empty(world * self.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
@@ -127,9 +145,11 @@ class GpuShardPrims:
             every = t
         raw = bytes(every.cpu().tolist())
         buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
-        check(self.lib.pdlp_shard_exchange_connect(self.h, C.cast(buf, C.c_void_p)))
-        if world > 1:
-            dist.barrier(group=group)              # every rank has mapped every block before the first flag is raised
+        try:
+            check(self.lib.pdlp_shard_exchange_connect(self.h, C.cast(buf, C.c_void_p)))
+        except Exception as exc:                       # noqa: BLE001
+            err = exc
+        agree(err)                                     # also the barrier: every rank has mapped every block
 
     def exchange_disconnect(self):
         check(self.lib.pdlp_shard_exchange_disconnect(self.h))
