@@ -133,6 +133,27 @@ typedef struct pdlp_plan_info {
 int pdlp_plan_inspect(const int32_t* host_rowptr, int64_t rows, int32_t value_bytes, int32_t sms,
                       pdlp_plan_info* host_out, int8_t* host_row_class);
 
+/* Host-side checker of the run layout (torchpdlp_b200/csrc/run_spmv.cuh; the layout of the two iteration kernels).
+ * Plans and packs a host CSR matrix (fp64) with the same planner and per-slot packer the device path uses, walks the
+ * chunks with a 32-lane emulation of the kernel's chunk walk and writes out = A x.  mode 0: the run layout (rows
+ * longer than long_row take the one-row-per-CTA path).  mode 1: the shared-memory panels of K^T
+ * (torchpdlp_b200/csrc/panel_spmv.cuh): panel boundaries, the panel matrix and its per-panel SELL plans are built as
+ * on the device path, every CTA's pieces are checked to lie in its own panel and to cover every (panel, row) once,
+ * and out = sum over panels of the partial sums (fails when x does not fit PANEL_MAX panels); then `chunks` counts
+ * pieces, `stream_entries` padded slots, `chunk_bytes` the largest piece, `max_warp_chunks` the sorting window.
+ * No GPU involved; used by tests/test_cpu_run_layout.py.
+ * Replaces nothing in the reference: torchPDLP's products are ATen calls
+ * (PDLP/primal_dual_hybrid_gradient_step.py:25,33,68,84). */
+typedef struct pdlp_run_info {
+  int64_t stream_entries; /* nonzeros + empty-row / long-row markers (all panels) */
+  int64_t rows_finished;  /* row epilogues the walk ran (mode 1: per panel); must equal rows */
+  int32_t grid, warps, chunks, long_rows;
+  int32_t panels, panel_cap, chunk_bytes, max_warp_chunks;
+} pdlp_run_info;
+int pdlp_run_emulate(const int32_t* host_rowptr, const int32_t* host_colidx, const double* host_vals, int64_t rows,
+                     int64_t cols, int32_t sms, int32_t long_row, int32_t mode, const double* host_x, double* host_out,
+                     pdlp_run_info* host_info);
+
 /* ---- lifetime -------------------------------------------------------------
  * Problem tuple (c, K, q, m_ineq, l, u): reference PDLP/util.py:239-269,
  * consumed at primal_dual_hybrid_gradient.py:7.  K is given as CSR (m x n) AND

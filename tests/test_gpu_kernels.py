@@ -173,6 +173,44 @@ def test_ruiz_matches_reference_pins(cfg1):
     eng.close()
 
 
+@pytest.mark.parametrize("which", ["cfg1", "bounds"])
+def test_pock_chambolle_matches_oracle(which, cfg1):
+    """pdlp_pock_chambolle (Ruiz, then alpha = 1 row / column L1 scaling: the `preconditioning` PDLP/main.py:8,107
+    imports but the snapshot does not define) against the oracle's restatement, orc.precondition(pock_chambolle=True).
+    No reference code exists for this function: parity is pinned to the oracle only."""
+    lp = cfg1 if which == "cfg1" else synthetic.mixed_bounds_lp()
+    op, c, q, l, u = oracle_parts(lp)
+    ops, c_s, q_s, l_s, u_s, sc = orc.precondition(op, c, q, l, u, pock_chambolle=True)
+    eng = make_engine(lp)
+    eng.ruiz(20, 1e-6)
+    eng.pock_chambolle()
+    D_row, D_col = (t.cpu().numpy() for t in eng.scaling())
+    gc, gq, gl, gu = (t.cpu().numpy() for t in eng.problem())
+    np.testing.assert_allclose(D_row, sc.D_row.numpy().ravel(), rtol=1e-12)
+    np.testing.assert_allclose(D_col, sc.D_col.numpy().ravel(), rtol=1e-12)
+    np.testing.assert_allclose(gc, c_s.numpy().ravel(), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(gq, q_s.numpy().ravel(), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(gl, l_s.numpy().ravel(), rtol=1e-12, atol=1e-300)      # +-inf stay +-inf
+    np.testing.assert_allclose(gu, u_s.numpy().ravel(), rtol=1e-12, atol=1e-300)
+    # both packed copies carry the scaled values: K_s v and K_s^T w through the hot-path layouts
+    rng = np.random.default_rng(1)
+    v, w = rng.normal(size=lp.n), rng.normal(size=lp.m)
+    tv, tw = torch.from_numpy(v), torch.from_numpy(w)
+    np.testing.assert_allclose(eng.spmv(v).cpu().numpy(), ops.mv(tv).numpy().ravel(), rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(eng.spmv(w, transpose=True).cpu().numpy(), ops.rmv(tw).numpy().ravel(), rtol=1e-10, atol=1e-11)
+    # ... including the iteration kernels' own copies (run chunks / panels): one fixed step on the scaled problem
+    x0, y0 = torch.from_numpy(rng.uniform(-1, 1, size=lp.n)), torch.from_numpy(np.abs(rng.normal(size=lp.m)))
+    ox, oy = orc.fixed_one_step_pdhg(x0.clone(), y0.clone(), c_s.reshape(-1), q_s.reshape(-1), ops, l_s.reshape(-1), u_s.reshape(-1),
+                                     lp.m_ineq, 0.05, 0.7, 1.0)
+    eng.set_iterate(x0, y0)
+    eng.set_step(0.05, 0.7, 1.0, adaptive=False)
+    eng.iterate(1, use_graph=False)
+    gx, gy = (t.cpu() for t in eng.get_iterate())
+    assert float((gx - ox.ravel()).abs().max()) <= 1e-11 * max(1.0, float(ox.abs().max()))
+    assert float((gy - oy.ravel()).abs().max()) <= 1e-11 * max(1.0, float(oy.abs().max()))
+    eng.close()
+
+
 def test_step_functions_reference_pins(cfg1, fp64_default):
     """The drop-in step functions against outputs of the EXECUTED reference."""
     from torchpdlp_b200 import primal_dual_hybrid_gradient_step as step
@@ -193,9 +231,14 @@ def test_step_functions_reference_pins(cfg1, fp64_default):
     assert j == 1
 
 
+@pytest.mark.parametrize("layout", ["sell", "run", "panel", "runpanel"])
 @pytest.mark.parametrize("which", ["cfg1", "ragged"])
-def test_loop_modes_bitwise_identical(which, cfg1):
-    """Eager launches, the CUDA graph and the persistent cooperative kernel give bit-identical iterates and scalars."""
+def test_loop_modes_bitwise_identical(which, layout, cfg1, monkeypatch):
+    """Eager launches, the CUDA graph and (SELL layout) the persistent cooperative kernel give bit-identical iterates
+    and scalars -- for each layout of the iteration kernels (PDLP_LAYOUT is read when the engine is created; the
+    panel kernel is forced on for these small matrices)."""
+    monkeypatch.setenv("PDLP_LAYOUT", layout)
+    monkeypatch.setenv("PDLP_PANEL_MIN_NNZ", "0")
     lp = cfg1 if which == "cfg1" else ragged_lp()
     outs = []
     for mode in (0, 1, 2):
@@ -213,6 +256,30 @@ def test_loop_modes_bitwise_identical(which, cfg1):
         eng.close()
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and o[2:] == outs[0][2:]
+
+
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_layouts_agree(which, cfg1, monkeypatch):
+    """The three layouts of the iteration kernels (SELL slices, row-major runs, runs + shared-memory panels of K^T)
+    sum the same products in different orders: 47 adaptive iterations agree to rounding."""
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    outs = []
+    monkeypatch.setenv("PDLP_PANEL_MIN_NNZ", "0")
+    for layout in ("sell", "run", "panel", "runpanel"):
+        monkeypatch.setenv("PDLP_LAYOUT", layout)
+        eng = make_engine(lp)
+        eng.set_iterate(None, None)
+        eng.set_step(0.05, 0.5, 1.0, adaptive=True)
+        eng.iterate(40, save_previous=True, use_graph=True)
+        eng.iterate(7, save_previous=False, use_graph=False)
+        x, y = eng.get_iterate()
+        outs.append((x.cpu(), y.cpu(), eng.state().eta))
+        eng.close()
+    for o in outs[1:]:
+        sx, sy = float(outs[0][0].abs().max()) + 1.0, float(outs[0][1].abs().max()) + 1.0
+        assert float((o[0] - outs[0][0]).abs().max()) <= 1e-10 * sx
+        assert float((o[1] - outs[0][1]).abs().max()) <= 1e-10 * sy
+        assert abs(o[2] - outs[0][2]) <= 1e-10 * abs(outs[0][2])
 
 
 def test_bitwise_reproducible(cfg1):

@@ -6,9 +6,12 @@ Tolerances.  Termination status, restart count n and restart kinds must match.  
 FIXED step the trajectory is insensitive to summation order: k and j must be equal and the
 objective agree to 1e-9 relative.  With the ADAPTIVE step the rule eta' = f(||dx||, ||dy||,
 dy^T K dx) amplifies last-bit differences: the reference's own dense and COO runs differ by
-4e-7 relative in the final objective, so the band is 2e-6 relative
-on the objective and one restart period (40) on k.
+4e-7 relative in the final objective; the band is north_star's 1e-6
+relative on the primal AND the (adjusted) dual objective, and one restart period (40) on k.
+The dual objective of every restart point is checked against the reference's printed lines
+(`[k] Primal Obj: ..., Adjusted Dual Obj: ...`, primal_dual_hybrid_gradient.py:167-170; 4 decimals).
 """
+ADAPTIVE_REL = 1e-6
 import json
 import os
 
@@ -58,11 +61,20 @@ def test_cfg1_against_executed_reference(run, cfg1):
     want = [({"Sufficient": 1, "Necessary": 2, "Artificial": 3}[a], 1 if c == "Average" else 0) for a, _, c in ref["restarts"]]
     assert kinds == want
     if o["adaptive"]:
-        assert abs(k - ref["k"]) <= 40 and rel(obj, ref["obj"]) < 2e-6, (k, ref["k"], obj, ref["obj"])
+        assert abs(k - ref["k"]) <= 40 and rel(obj, ref["obj"]) < ADAPTIVE_REL, (k, ref["k"], obj, ref["obj"])
     else:
         assert (k, j) == (ref["k"], ref["j"])
         assert rel(obj, ref["obj"]) < 1e-9, (obj, ref["obj"])
     assert x.shape == (cfg1.n, 1) and x.is_cuda
+    # primal and adjusted dual objective of every restart point against the lines the reference printed (:167-170)
+    assert len(info["trace"]) == len(ref["lines"])
+    for chk, line in zip(info["trace"], ref["lines"]):
+        p_ref, d_ref = float(line[1]), float(line[2])
+        band = (ADAPTIVE_REL if o["adaptive"] else 1e-9)
+        assert abs(chk.point.prim_obj - p_ref) <= 0.51e-4 + band * abs(p_ref), (line, chk.point.prim_obj)
+        assert abs(chk.point.adj_dual - d_ref) <= 0.51e-4 + band * abs(d_ref), (line, chk.point.adj_dual)
+        if not o["adaptive"]:
+            assert int(line[0]) == chk.k
 
 
 BOUNDS_RUNS = load("bounds_reference.json")["runs"]
@@ -138,9 +150,14 @@ def test_cfg2_full_size_against_oracle(idx):
                                                 primal_weight=o.get("primal_update", False))
     assert status == run["status"] and n == run["n"]
     if o.get("adaptive"):
-        assert abs(k - run["k"]) <= 40 and rel(obj, run["obj"]) < 2e-6, (k, run["k"], obj, run["obj"])
+        assert abs(k - run["k"]) <= 40 and rel(obj, run["obj"]) < ADAPTIVE_REL, (k, run["k"], obj, run["obj"])
     else:
         assert (k, j) == (run["k"], run["j"]) and rel(obj, run["obj"]) < 1e-9
+    # dual side: the adjusted dual objective (helpers.py:84) of every restart point against the oracle's trace
+    band = ADAPTIVE_REL if o.get("adaptive") else 1e-9
+    assert len(info["trace"]) == len(run["trace"])
+    for chk, t in zip(info["trace"], run["trace"]):
+        assert rel(chk.point.prim_obj, t["prim_obj"]) < band and rel(chk.point.adj_dual, t["adj_dual"]) < band, (t, chk.point.adj_dual)
     # size-independent property: the returned point satisfies the reference's termination test
     xv = x.reshape(-1).cpu().numpy()
     r = lp.K @ xv - lp.q
@@ -324,3 +341,57 @@ def test_cfg4_full_size_properties():
     r = lp.K @ xv - lp.q
     viol = np.concatenate([r[lp.m_ineq:], np.minimum(r[:lp.m_ineq], 0.0)])
     assert rel(float(np.linalg.norm(viol)), info["trace"][-1].point.pr) < 1e-9
+
+
+def test_pdlp_solver_on_an_mps_file(capsys):
+    """The importable one-call entry of the reference's older line (Packages/PDLP_without_presolve_infeasibility.py:
+    747-789): same arguments, 5-tuple (minimizer, objective, k, n, j), minimizer in the ORIGINAL variables."""
+    import scipy.optimize
+    import torchpdlp_b200
+    from torchpdlp_b200.util import mps_to_standard_form
+    path = os.path.join(GOLD, "small_generated.mps")
+    torch.manual_seed(0)
+    x, obj, k, n, j = torchpdlp_b200.pdlp_solver(path, tol=1e-6, verbose=False)
+    c, K, q, m_ineq, l, u = mps_to_standard_form(path, device="cpu")
+    Kd = K.to_dense().numpy()
+    cv, qv = c.numpy().ravel(), q.numpy().ravel()
+    ref = scipy.optimize.linprog(cv, A_ub=-Kd[:m_ineq], b_ub=-qv[:m_ineq], A_eq=Kd[m_ineq:], b_eq=qv[m_ineq:],
+                                 bounds=list(zip(l.numpy().ravel(), u.numpy().ravel())), method="highs")
+    assert ref.status == 0
+    xv = x.cpu().numpy().ravel()
+    assert x.shape == (Kd.shape[1], 1) and x.is_cuda and k > 0 and n > 0 and j > k
+    assert abs(obj - ref.fun) <= 1e-4 * (1 + abs(ref.fun))
+    assert abs(float(cv @ xv) - obj) <= 1e-9 * (1 + abs(obj))            # x is in the original variables
+    r = Kd @ xv - qv
+    assert np.linalg.norm(np.concatenate([r[m_ineq:], np.minimum(r[:m_ineq], 0)])) <= 1e-5 * (1 + np.linalg.norm(qv))
+    x2, obj2, *_ = torchpdlp_b200.pdlp_solver(path, tol=1e-6, verbose=True, precondition=False, adaptive_step=False,
+                                               primal_update=False)
+    assert abs(obj2 - ref.fun) <= 1e-4 * (1 + abs(ref.fun))
+    assert "Objective Value:" in capsys.readouterr().out
+
+
+def test_engine_cache_never_serves_a_stale_problem(cfg1):
+    """Two different same-shaped LPs back to back, and an in-place edit of q between two solves, must each be solved
+    as given (the functional entry points look their engine up in torchpdlp_b200/_cache.py)."""
+    from torchpdlp_b200 import _cache
+    from torchpdlp_b200.primal_dual_hybrid_gradient import pdlp_algorithm
+    torch.set_default_dtype(torch.float64)
+    _cache.clear()
+    objs = []
+    for seed in (0, 1):
+        lp = synthetic.feasible_lp(seed=seed)
+        c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr", device="cuda")
+        torch.manual_seed(0)
+        objs.append(pdlp_algorithm(K, m_ineq, c, q, l, u, "cuda", verbose=False, adaptive=True)[1])
+        del c, K, q, l, u                      # the next LP may be allocated on the same addresses
+    assert rel(objs[0], objs[1]) > 1e-3        # different problems, different optima
+    lp = synthetic.feasible_lp(seed=0)
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr", device="cuda")
+    torch.manual_seed(0)
+    a = pdlp_algorithm(K, m_ineq, c, q, l, u, "cuda", verbose=False, adaptive=True)[1]
+    assert rel(a, objs[0]) < 1e-12             # same LP as the first one: same answer
+    q.mul_(1.05)                               # in place: same tensor object, same address
+    torch.manual_seed(0)
+    b = pdlp_algorithm(K, m_ineq, c, q, l, u, "cuda", verbose=False, adaptive=True)[1]
+    assert rel(a, b) > 1e-4
+    _cache.clear()

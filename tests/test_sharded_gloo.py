@@ -25,7 +25,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, adaptive, primal_update, out, exchange="nccl"):
+def _worker(rank, world, port, adaptive, primal_update, out, exchange="nccl", time_limit=3600.0, skew=0.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_default_dtype(torch.float64)
@@ -39,7 +39,13 @@ def _worker(rank, world, port, adaptive, primal_update, out, exchange="nccl"):
     prims = FakeShardPrims(lp.K[r0:r1], mi_local, lp.c, lp.q[r0:r1], lp.l, lp.u)
     solver = ShardedSolver(prims, exchange=exchange)
     torch.manual_seed(0)
-    x, y_local, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=primal_update)
+    if skew:                             # this rank's clock runs ahead: it alone would see the limit one block early
+        import time as _time
+        import types
+        import torchpdlp_b200.primal_dual_hybrid_gradient as drv
+        drv.time = types.SimpleNamespace(time=lambda: _time.time() + (skew if rank == 1 else 0.0))   # the loop's clock only
+    x, y_local, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=primal_update,
+                                                                 time_limit=time_limit)
     ys = [torch.zeros(int(cuts[i + 1] - cuts[i])) for i in range(world)] if rank == 0 else None
     dist.gather(y_local, ys, dst=0)
     if rank == 0:
@@ -52,11 +58,11 @@ def _worker(rank, world, port, adaptive, primal_update, out, exchange="nccl"):
     dist.destroy_process_group()
 
 
-def run_world(world, adaptive, primal_update, exchange="nccl"):
+def run_world(world, adaptive, primal_update, exchange="nccl", time_limit=3600.0, skew=0.0):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, adaptive, primal_update, out, exchange))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, adaptive, primal_update, out, exchange, time_limit, skew))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -88,7 +94,8 @@ def test_two_rank_solve_matches_oracle(adaptive, primal_update):
         np.testing.assert_allclose(res["y"], sol.y.numpy(), rtol=0, atol=1e-9)
     assert abs(res["sigma"] - sol.sigma_max) <= 1e-9 * sol.sigma_max
     # one exchange per iteration + 4 per restart test + setup (norm, 2 per power-iteration round + 1)
-    assert res["collectives"] == res["k"] + 4 * (res["k"] // 40) + 1 + 100 + 1
+    # ... + one time-limit agreement per block of iterations
+    assert res["collectives"] == res["k"] + 5 * (res["k"] // 40) + 1 + 100 + 1
 
 
 def test_two_rank_peer_exchange_orchestration():
@@ -100,7 +107,17 @@ def test_two_rank_peer_exchange_orchestration():
     assert (a["k"], a["n"], a["j"], a["status"]) == (b["k"], b["n"], b["j"], b["status"])
     assert a["obj"] == b["obj"] and np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"])
     # everything after the initial ||q|| norm (issued before the exchange is connected) is a peer-memory exchange
-    assert b["p2p_exchanges"] == b["collectives"] - 1 == b["k"] + 4 * (b["k"] // 40) + 100 + 1
+    assert b["p2p_exchanges"] == b["collectives"] - 1 == b["k"] + 5 * (b["k"] // 40) + 100 + 1
+
+
+def test_time_limit_is_a_collective_decision():
+    """The ranks' clocks disagree (rank 1 runs 1000 s ahead of a 500 s limit): every rank must leave the loop in the
+    same block with the reference's status string, and the teardown collectives still match (no hang: the workers
+    exit 0).  Without the agreement rank 1 would stop alone and rank 0 would wait in the next exchange."""
+    res = run_world(2, False, False, time_limit=500.0, skew=1000.0)
+    assert res["status"] == "Unsolved (Time limit exceeded)" and res["k"] == 0 and res["n"] == 0
+    res = run_world(2, False, False, "p2p", time_limit=500.0, skew=1000.0)
+    assert res["status"] == "Unsolved (Time limit exceeded)" and res["k"] == 0
 
 
 def test_partition_rows_balances_nnz():

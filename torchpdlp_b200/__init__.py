@@ -18,6 +18,9 @@ def __getattr__(name):
     if name == "pdlp_algorithm":
         from .primal_dual_hybrid_gradient import pdlp_algorithm
         return pdlp_algorithm
+    if name == "pdlp_solver":
+        from .primal_dual_hybrid_gradient import pdlp_solver
+        return pdlp_solver
     if name == "Engine":
         from .engine import Engine
         return Engine

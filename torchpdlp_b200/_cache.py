@@ -2,62 +2,155 @@
 
 torchPDLP's step / helper functions take the LP tensors on every call
 (PDLP/primal_dual_hybrid_gradient_step.py:3, PDLP/helpers.py:53,98).  The engine
-keeps the LP resident on the GPU instead, so the functional wrappers find (or
-build) the engine for a given (K, c, q, l, u) through this small cache.
+keeps its own copy of the LP resident on the GPU instead, so the functional wrappers
+find (or build) the engine for a given (K, c, q, l, u) through this small cache.
+
+An entry is only ever reused for the very tensors it was built from, unmodified: the
+cache holds weak references to the source tensors and their version counters, so
+
+* a different tensor that happens to land on a freed tensor's address (the CUDA caching
+  allocator recycles blocks between the instances of a ``main.py`` run) is a miss,
+* an in-place edit of any source tensor (``q.mul_(2)``) is a miss,
+* an engine is closed -- its GPU memory released -- as soon as one of its source
+  tensors is garbage collected, and at most ``_MAX`` engines stay resident.
 """
 from __future__ import annotations
 
+import weakref
 from collections import OrderedDict
 
 import torch
 
 from .engine import Engine
 
-_MAX = 4
-_engines: "OrderedDict[tuple, Engine]" = OrderedDict()
+_MAX = 2
+_entries: "OrderedDict[int, _Entry]" = OrderedDict()
+_next_id = 0
 
 
-def _ptr(t) -> int:
-    if not isinstance(t, torch.Tensor):
-        return id(t)
-    if t.layout == torch.sparse_coo:
-        return t._values().data_ptr()
-    if t.layout == torch.sparse_csr:
-        return t.values().data_ptr()
-    return t.data_ptr()
+def _payload(t):
+    """The tensor whose version counter moves when the data of ``t`` is edited in place."""
+    if isinstance(t, torch.Tensor):
+        if t.layout == torch.sparse_coo:
+            return t._values()
+        if t.layout == torch.sparse_csr:
+            return t.values()
+    return t
 
 
-def signature(K, c, q, l, u, m_ineq) -> tuple:
-    shape = tuple(K.shape)
-    return (_ptr(K), shape, _ptr(c), _ptr(q), _ptr(l), _ptr(u), int(m_ineq))
+def _version(t) -> int:
+    p = _payload(t)
+    return int(p._version) if isinstance(p, torch.Tensor) else 0
+
+
+class _Snap:
+    """Identity + version of one source object (tensor, scipy matrix, numpy array)."""
+
+    __slots__ = ("ref", "strong", "version")
+
+    def __init__(self, obj, keep_alive=False):
+        try:
+            self.ref = weakref.ref(obj)
+            self.strong = obj if keep_alive else None
+        except TypeError:                      # not weak-referenceable (e.g. a tuple): keep it alive instead
+            self.ref = None
+            self.strong = obj
+        self.version = _version(obj)
+
+    def get(self):
+        return self.strong if self.ref is None else self.ref()
+
+    def matches(self, obj) -> bool:
+        return self.get() is obj and self.version == _version(obj)
+
+
+class _Entry:
+    def __init__(self, engine, K, vectors, m_ineq, keep_alive=False):
+        self.engine = engine
+        self.K = _Snap(K, keep_alive)
+        self.vectors = [_Snap(v, keep_alive) for v in vectors]
+        self.m_ineq = int(m_ineq)
+
+    def alive(self) -> bool:
+        return bool(self.engine.h) and self.K.get() is not None and all(s.get() is not None for s in self.vectors)
+
+    def matches(self, K, vectors, m_ineq) -> bool:
+        return (self.m_ineq == int(m_ineq) and self.K.matches(K)
+                and all(s.matches(v) for s, v in zip(self.vectors, vectors)))
+
+
+def _drop(key) -> None:
+    ent = _entries.pop(key, None)
+    if ent is not None:
+        ent.engine.close()
+
+
+def _sweep() -> None:
+    for key in [k for k, e in _entries.items() if not e.alive()]:
+        _drop(key)
+
+
+def _insert(ent: _Entry) -> None:
+    global _next_id
+    _sweep()
+    key = _next_id
+    _next_id += 1
+    _entries[key] = ent
+    # release the GPU copy as soon as a source tensor dies (not only at the next lookup)
+    for snap in [ent.K] + ent.vectors:
+        obj = snap.get()
+        if snap.ref is not None and snap.strong is None and obj is not None:
+            try:
+                weakref.finalize(obj, _drop, key)
+            except TypeError:
+                pass
+    while len(_entries) > _MAX:
+        _drop(next(iter(_entries)))
 
 
 def attach(K, engine: Engine, c, q, l, u, m_ineq) -> None:
     """Remember that ``engine`` already holds exactly (K, c, q, l, u)."""
-    sig = signature(K, c, q, l, u, m_ineq)
-    _engines[sig] = engine
-    _engines.move_to_end(sig)
-    while len(_engines) > _MAX:
-        _, old = _engines.popitem(last=False)
-        old.close()
+    _insert(_Entry(engine, K, (c, q, l, u), m_ineq))
+
+
+def _resolve_device(K, device):
+    if device is None or (isinstance(device, str) and device in ("cpu", "auto", "gpu")) or \
+            (isinstance(device, torch.device) and device.type != "cuda"):
+        return K.device if isinstance(K, torch.Tensor) and K.device.type == "cuda" else "cuda"
+    return device
 
 
 def engine_for(K, m_ineq, c, q, l, u, device=None) -> Engine:
-    sig = signature(K, c, q, l, u, m_ineq)
-    eng = _engines.get(sig)
-    if eng is not None and eng.h:
-        _engines.move_to_end(sig)
-        return eng
-    if device is None or (isinstance(device, str) and device in ("cpu", "auto", "gpu")) or \
-            (isinstance(device, torch.device) and device.type != "cuda"):
-        device = K.device if isinstance(K, torch.Tensor) and K.device.type == "cuda" else "cuda"
+    _sweep()
+    for key, ent in _entries.items():
+        if ent.matches(K, (c, q, l, u), m_ineq):
+            _entries.move_to_end(key)
+            return ent.engine
     dtype = K.dtype if isinstance(K, torch.Tensor) else None
-    eng = Engine(K, m_ineq, c, q, l, u, device=device, dtype=dtype)
+    eng = Engine(K, m_ineq, c, q, l, u, device=_resolve_device(K, device), dtype=dtype)
     attach(K, eng, c, q, l, u, m_ineq)
     return eng
 
 
+def engine_for_matrix(K, device=None) -> Engine:
+    """An engine whose matrix is ``K`` (any vectors): enough for products and the power iteration
+    (PDLP/helpers.py:41-51 takes only K).  Built with zero vectors, which the entry keeps alive."""
+    _sweep()
+    for key, ent in _entries.items():
+        if ent.K.matches(K):
+            _entries.move_to_end(key)
+            return ent.engine
+    dtype = K.dtype if isinstance(K, torch.Tensor) else torch.float64
+    zn = torch.zeros(K.shape[1], dtype=dtype)
+    zm = torch.zeros(K.shape[0], dtype=dtype)
+    eng = Engine(K, 0, zn, zm, zn, zn, device=_resolve_device(K, device), dtype=dtype)
+    ent = _Entry(eng, K, (zn, zm, zn, zn), 0)
+    for s in ent.vectors:                      # the placeholders live as long as the entry
+        s.strong = s.get()
+    _insert(ent)
+    return eng
+
+
 def clear() -> None:
-    while _engines:
-        _, e = _engines.popitem()
-        e.close()
+    for key in list(_entries):
+        _drop(key)

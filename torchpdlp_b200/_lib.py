@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("PDLP_B200_LIB") or os.path.join(HERE, "libpdlp_b200.so")   # env: developer sweeps only
 SOURCES = [os.path.join(HERE, "csrc", "pdlp_b200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "stream_spmv.cuh"), os.path.join(HERE, "csrc", "pdlp_ops.cuh"),
-           os.path.join(ROOT, "include", "pdlp_b200.h")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("stream_spmv.cuh", "run_spmv.cuh", "panel_spmv.cuh", "pdlp_ops.cuh", "pdlp_block.cuh")] + \
+          [os.path.join(ROOT, "include", "pdlp_b200.h")]
 
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-O3", "-std=c++17"]
@@ -61,6 +61,12 @@ class PlanInfo(C.Structure):
                 ("covered_once", C.c_int32), ("ranges_ok", C.c_int32)]
 
 
+class RunInfo(C.Structure):
+    _fields_ = [("stream_entries", C.c_int64), ("rows_finished", C.c_int64), ("grid", C.c_int32), ("warps", C.c_int32),
+                ("chunks", C.c_int32), ("long_rows", C.c_int32), ("panels", C.c_int32), ("panel_cap", C.c_int32),
+                ("chunk_bytes", C.c_int32), ("max_warp_chunks", C.c_int32)]
+
+
 _P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SYMBOLS = {
     "pdlp_last_error": (C.c_char_p, []),
@@ -92,6 +98,8 @@ SYMBOLS = {
     "pdlp_batch_step": (_I, [_P, _P, _P, _P, _D, _D]),
     "pdlp_batch_gap": (_I, [_P, _P, _P, C.POINTER(_D)]),
     "pdlp_plan_inspect": (_I, [_P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(PlanInfo), _P]),
+    "pdlp_run_emulate": (_I, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                              C.POINTER(RunInfo)]),
     "pdlp_shard_enable": (_I, [_P, _D, _D]),
     "pdlp_shard_kty": (_I, [_P, _P]),
     "pdlp_shard_step": (_I, [_P, _P, _I]),

@@ -15,6 +15,8 @@
 #include "../../include/pdlp_b200.h"
 #include "pdlp_block.cuh"
 #include "pdlp_ops.cuh"
+#include "panel_spmv.cuh"
+#include "run_spmv.cuh"
 
 using namespace pdlp;
 
@@ -50,8 +52,8 @@ struct HostSell {
   int sigma = 0;                       // sorting window the cost model chose
 };
 
-static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int value_bytes, int W, int KB, int sigma,
-                                int long_row, int warp_row, int max_grid) {
+static HostSell build_sell_plan(const int* rowptr, int rows, int value_bytes, int W, int KB, int sigma,
+                                int long_row, int warp_row, int max_grid, double epi_sectors = 6.0) {
   HostSell P;
   auto len = [&](int r) { return rowptr[r + 1] - rowptr[r]; };
   // three classes of rows: one per lane (SELL slices), one per warp (32 equal segments, one per lane: the heavy
@@ -88,7 +90,7 @@ static HostSell build_sell_plan(const std::vector<int>& rowptr, int rows, int va
     // measured share of epilogue accesses that fetch their own 32-byte sector from L2 (configs 2 and 4, K and K^T:
     // sigma = 128 / 256 / 1024 -> 36.7 / 39.1 / 41.2 us for K1 of config 2, 282 / 293 / 363 us for K1 of config 4).
     auto g = [](int cand) { return cand <= 128 ? 0.25 : cand <= 256 ? 0.35 : cand <= 512 ? 0.6 : 1.0; };
-    const double epi_bytes = 6 * 32.0;
+    const double epi_bytes = epi_sectors * 32.0;    // scattered vector accesses of the row epilogue
     double best_cost = 0.0;
     int best = sigma;
     long long nnz_short = 0;
@@ -250,6 +252,318 @@ __global__ void pack_kernel(const Piece* pieces, const int* perm, int npieces, c
 }
 
 // ---------------------------------------------------------------------------
+// plan of the run layout (run_spmv.cuh): stream positions, chunk descriptors, per-warp chunk ranges
+// ---------------------------------------------------------------------------
+// A chunk covers stream positions [gp0, gp0 + CHUNK) of its (panel's) stream, clipped to gp_limit: the tail behind
+// gp_limit is zero padding.  Chunks end where a warp's row range ends and where a long row (one row per CTA, not in
+// the stream) interrupts the sequence of rows, so that the rows finishing inside a chunk are always consecutive.
+struct ChunkDesc {
+  int gp0, gp_limit, panel, pad;
+};
+
+struct HostRun {
+  std::vector<int> sptr;               // rows + 1: stream position of each row's first entry
+  std::vector<int> warp_chunk_begin;   // grid * W + 1
+  std::vector<ChunkDesc> chunks;
+  std::vector<int> long_rows;
+  int grid = 1;
+  bool ok = true;
+};
+
+// Warps [w0, w0 + nwarps) share rows [0, rows) of one stream (sptr): contiguous row ranges balanced by entries, cut
+// into chunks.  `breaks`: sorted rows that interrupt the stream (long rows), or nullptr.
+static void run_cut_warps(const int* sptr, int rows, int chunk, int w0, int nwarps, int nused, int panel,
+                          const std::vector<int>* breaks, std::vector<int>& wcb, std::vector<ChunkDesc>& chunks) {
+  const long long total = sptr[rows];
+  int r_prev = 0;
+  size_t bi = 0;
+  for (int w = 0; w < nwarps; ++w) {
+    int r = rows;
+    if (w + 1 < nused) {
+      const long long target = total * (w + 1) / nused;
+      r = (int)(std::lower_bound(sptr, sptr + rows + 1, (int)target) - sptr);
+      r = std::min(std::max(r, r_prev), rows);
+    } else if (w + 1 < nwarps && w + 1 > nused) {
+      r = rows;
+    }
+    wcb[w0 + w] = (int)chunks.size();
+    // segments of [r_prev, r) between the long rows
+    int seg_begin = r_prev;
+    while (seg_begin < r) {
+      while (breaks && bi < breaks->size() && (*breaks)[bi] < seg_begin) ++bi;
+      int seg_end = r;
+      if (breaks && bi < breaks->size() && (*breaks)[bi] < r) seg_end = (*breaks)[bi];
+      for (int gp = sptr[seg_begin]; gp < sptr[seg_end]; gp += chunk) chunks.push_back(ChunkDesc{gp, sptr[seg_end], panel, 0});
+      seg_begin = seg_end == r ? r : seg_end + 1;
+    }
+    r_prev = r;
+  }
+  wcb[w0 + nwarps] = (int)chunks.size();
+}
+
+static HostRun build_run_plan(const int* rowptr, int rows, int long_row, int max_grid, int W, int chunk) {
+  HostRun P;
+  P.sptr.resize((size_t)rows + 1);
+  long long pos = 0;
+  for (int r = 0; r < rows; ++r) {
+    P.sptr[r] = (int)pos;
+    const int len = rowptr[r + 1] - rowptr[r];
+    if (len > long_row) P.long_rows.push_back(r);      // not in the stream
+    else pos += std::max(1, len);                       // an empty row is one zero entry
+  }
+  if (pos >= 0x7fffffffLL - chunk) { P.ok = false; return P; }
+  P.sptr[rows] = (int)pos;
+  const int nused = (int)std::max<long long>(1, std::min<long long>((long long)max_grid * W, (pos + chunk - 1) / chunk));
+  P.grid = std::max(1, (nused + W - 1) / W);
+  if (!P.long_rows.empty()) P.grid = std::max(P.grid, std::min(max_grid, (int)P.long_rows.size()));
+  const int nw = P.grid * W;
+  P.warp_chunk_begin.assign((size_t)nw + 1, 0);
+  run_cut_warps(P.sptr.data(), rows, chunk, 0, nw, nused, 0, &P.long_rows, P.warp_chunk_begin, P.chunks);
+  return P;
+}
+
+// the row that holds stream position gp: sptr[row] <= gp < sptr[row + 1] (rows outside the stream have no positions)
+__host__ __device__ inline int run_row_of(const int* sptr, int rows, int gp) {
+  int lo = 0, hi = rows;             // invariant: sptr[lo] <= gp < sptr[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (sptr[mid] <= gp) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// One slot of a chunk of the plain layout.  Returns whether the slot is the last entry of its row; *row = its row
+// (-1 for padding).  Host and device: the device packers call it per thread, pdlp_run_emulate on the CPU.
+template <typename T, typename CT>
+__host__ __device__ inline bool run_pack_slot(const ChunkDesc& d, int s, int rows, const int* sptr, const int* rowptr,
+                                              const int* colidx, const T* vals, unsigned char* blk, int* row) {
+  using Cfg = RunCfg<T, CT>;
+  T* vdst = reinterpret_cast<T*>(blk);
+  CT* cdst = reinterpret_cast<CT*>(blk + Cfg::VALS_BYTES);
+  const int gp = d.gp0 + s;
+  const int at = (s % Cfg::E) * 32 + s / Cfg::E;          // lane s / E, step s % E
+  *row = -1;
+  if (gp >= d.gp_limit) {                                // zero padding
+    vdst[at] = T(0);
+    cdst[at] = (CT)0;
+    return false;
+  }
+  const int r = run_row_of(sptr, rows, gp), off = gp - sptr[r];
+  const int len = rowptr[r + 1] - rowptr[r];
+  *row = r;
+  if (len == 0) {                                        // empty row: one zero entry
+    vdst[at] = T(0);
+    cdst[at] = Cfg::END;
+    return true;
+  }
+  const int src = rowptr[r] + off;
+  const bool end = off == len - 1;
+  vdst[at] = vals[src];
+  cdst[at] = (CT)((CT)colidx[src] | (end ? Cfg::END : (CT)0));
+  return end;
+}
+
+// per-lane words and the trailer of a chunk from the END flags of its CHUNK slots (stream order); host version
+template <int E>
+static void run_pack_meta_host(const unsigned char* ends, int row0, unsigned* meta, RunTrailer* tr) {
+  int below = 0;
+  unsigned any_steps = 0, F = 0;
+  for (int lane = 0; lane < 32; ++lane) {
+    unsigned endm = 0;
+    for (int k = 0; k < E; ++k) endm |= (ends[lane * E + k] ? 1u : 0u) << k;
+    meta[lane] = endm | ((unsigned)below << 8);
+    below += __builtin_popcount(endm);
+    any_steps |= endm;
+    if (endm) F |= 1u << lane;
+  }
+  *tr = RunTrailer{row0, below, any_steps, F};
+}
+
+// device: threads 0..31 of the block (one warp), after the END flags of all slots are in shared memory
+template <int E>
+__device__ inline void run_pack_meta_dev(const unsigned char* ends, int row0, unsigned* meta, RunTrailer* tr) {
+  const int lane = threadIdx.x;
+  unsigned endm = 0;
+#pragma unroll
+  for (int k = 0; k < E; ++k) endm |= (ends[lane * E + k] ? 1u : 0u) << k;
+  const int cnt = __popc(endm);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  unsigned any_steps = endm;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) any_steps |= __shfl_xor_sync(0xffffffffu, any_steps, o);
+  const unsigned F = __ballot_sync(0xffffffffu, endm != 0);
+  const int nrows = __shfl_sync(0xffffffffu, incl, 31);
+  meta[lane] = endm | ((unsigned)(incl - cnt) << 8);
+  if (lane == 0) *tr = RunTrailer{row0, nrows, any_steps, F};
+}
+
+// one CTA (CHUNK threads) per chunk
+template <typename T>
+__global__ void run_pack_kernel(const ChunkDesc* desc, int nchunks, int rows, const int* sptr, const int* rowptr,
+                                const int* colidx, const T* vals, unsigned char* chunks) {
+  using CT = uint32_t;
+  using Cfg = RunCfg<T, CT>;
+  __shared__ unsigned char s_end[Cfg::CHUNK];
+  __shared__ int s_row0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const ChunkDesc d = desc[c];
+    unsigned char* blk = chunks + (size_t)c * Cfg::CHUNK_BYTES;
+    for (int s = threadIdx.x; s < Cfg::CHUNK; s += blockDim.x) {
+      int row;
+      const bool end = run_pack_slot<T, CT>(d, s, rows, sptr, rowptr, colidx, vals, blk, &row);
+      s_end[s] = end ? 1 : 0;
+      if (s == 0) s_row0 = row;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+      run_pack_meta_dev<Cfg::E>(s_end, s_row0, reinterpret_cast<unsigned*>(blk + Cfg::VALS_BYTES + Cfg::COLS_BYTES),
+                                reinterpret_cast<RunTrailer*>(blk + Cfg::VALS_BYTES + Cfg::COLS_BYTES + Cfg::META_BYTES));
+    __syncthreads();
+  }
+}
+
+// ---- shared-memory panels of K^T (panel_spmv.cuh) ----
+constexpr int PANEL_MAX = 16;
+struct HostPanel {
+  int P = 0, grid = 0, panel_cap = 0;
+  std::vector<int> panel_begin;        // P + 1
+  std::vector<int> cta_panel;          // grid
+  std::vector<int> rowptr;             // P * rows + 1: the panel matrix (row p * rows + r = entries of row r in panel p)
+  HostSell sell;                       // its SELL plan, every panel planned for its own CTAs
+};
+
+// cnt[p * rows + r] = entries of row r whose column lies in panel p
+__global__ void panel_count_kernel(const int* rowptr, const int* colidx, int rows, const int* panel_begin, int P, int* cnt) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    int c[PANEL_MAX];
+#pragma unroll
+    for (int p = 0; p < PANEL_MAX; ++p) c[p] = 0;
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const int col = colidx[e];
+#pragma unroll
+      for (int p = 0; p < PANEL_MAX; ++p)
+        if (p < P && col >= panel_begin[p] && col < panel_begin[p + 1]) ++c[p];
+    }
+#pragma unroll
+    for (int p = 0; p < PANEL_MAX; ++p)
+      if (p < P) cnt[(size_t)p * rows + r] = c[p];
+  }
+}
+
+// CSR arrays of the panel matrix from the matrix's own: entries keep their order inside a row, columns become
+// panel-relative.  colidx_out may be null (values only: after a scaling pass).
+template <typename T>
+__global__ void panel_fill_kernel(const int* rowptr, const int* colidx, const T* vals, int rows, const int* panel_begin,
+                                  int P, const int* prowptr, int* colidx_out, T* vals_out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    int cur[PANEL_MAX];
+#pragma unroll
+    for (int p = 0; p < PANEL_MAX; ++p) cur[p] = p < P ? prowptr[(size_t)p * rows + r] : 0;
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const int col = colidx[e];
+      const T v = vals[e];
+#pragma unroll
+      for (int p = 0; p < PANEL_MAX; ++p)
+        if (p < P && col >= panel_begin[p] && col < panel_begin[p + 1]) {
+          if (colidx_out) colidx_out[cur[p]] = col - panel_begin[p];
+          vals_out[cur[p]] = v;
+          ++cur[p];
+        }
+    }
+  }
+}
+
+// panel boundaries: P panels over `cols` gathered elements, CTA counts as even as possible, boundaries (multiples of
+// 4) placed so that a panel's share of the nonzeros matches its share of the CTAs.  col_nnz_prefix: cols + 1 entries.
+static bool panel_boundaries(const int* col_nnz_prefix, int cols, int value_bytes, int sms, HostPanel& H) {
+  const int cap = std::min(32760, (int)(PDLP_PANEL_BYTES / value_bytes)) / 4 * 4;
+  for (int P = std::max(1, (cols + cap - 1) / cap); P <= PANEL_MAX && P <= sms; ++P) {
+    std::vector<int> ctas(P, sms / P);
+    for (int p = 0; p < sms % P; ++p) ++ctas[p];
+    std::vector<int> pb(P + 1, 0);
+    pb[P] = cols;
+    const long long nnz = col_nnz_prefix[cols];
+    long long cum = 0;
+    bool fits = true;
+    for (int p = 1; p < P; ++p) {
+      cum += ctas[p - 1];
+      const long long target = nnz * cum / sms;
+      int b = (int)(std::lower_bound(col_nnz_prefix, col_nnz_prefix + cols + 1, (int)target) - col_nnz_prefix);
+      b = std::min(cols, (b + 2) / 4 * 4);
+      pb[p] = std::max(b, pb[p - 1]);
+    }
+    for (int p = 0; p < P; ++p) fits = fits && (pb[p + 1] - pb[p] <= cap);
+    if (!fits) {                            // skewed columns: equal-width panels instead
+      const int width = ((cols + P - 1) / P + 3) / 4 * 4;
+      fits = width <= cap;
+      for (int p = 1; p < P; ++p) pb[p] = std::min(cols, p * width);
+    }
+    if (!fits) continue;
+    H.P = P;
+    H.grid = sms;
+    H.panel_begin = pb;
+    H.cta_panel.clear();
+    for (int p = 0; p < P; ++p) H.cta_panel.insert(H.cta_panel.end(), ctas[p], p);
+    int widest = 0;
+    for (int p = 0; p < P; ++p) widest = std::max(widest, pb[p + 1] - pb[p]);
+    H.panel_cap = (widest + 3) / 4 * 4 + 4;
+    return true;
+  }
+  return false;
+}
+
+// The panel matrix and its SELL plan from the per-(panel, row) entry counts.  Every panel is planned on its own (its
+// rows sorted and cut into slices, its pieces split over the warps of ITS CTAs) and the plans are concatenated, so
+// that CTA b only ever touches pieces of panel cta_panel[b].  The row epilogue of a panel row is one scattered
+// 8-byte store, hence the small epilogue weight: the cost model goes for wide sorting windows (little padding).
+static bool panel_plan(const int* cnt, int rows, int value_bytes, int W, int KB, HostPanel& H) {
+  const int P = H.P;
+  H.rowptr.assign((size_t)P * rows + 1, 0);
+  long long pos = 0;
+  for (size_t i = 0; i < (size_t)P * rows; ++i) {
+    H.rowptr[i] = (int)pos;
+    pos += cnt[i];
+  }
+  if (pos >= 0x7fffffffLL) return false;
+  H.rowptr[(size_t)P * rows] = (int)pos;
+  HostSell& S = H.sell;
+  S = HostSell();
+  S.warp_begin.assign((size_t)H.grid * W + 1, 0);
+  int cta = 0;
+  for (int p = 0; p < P; ++p) {
+    int n = 0;
+    while (cta + n < H.grid && H.cta_panel[cta + n] == p) ++n;
+    const char* sg = getenv("PDLP_PANEL_SIGMA");      // developer knob: smallest sorting window considered
+    HostSell Q = build_sell_plan(H.rowptr.data() + (size_t)p * rows, rows, value_bytes, W, KB, sg ? atoi(sg) : PDLP_SIGMA,
+                                 PDLP_LONG_ROW, PDLP_WARP_ROW, n, 1.0);
+    if (!Q.long_rows.empty() || Q.packed_bytes % 16 != 0) return false;      // (a row part of > LONG_ROW entries: not here)
+    const int piece0 = (int)S.pieces.size(), perm0 = (int)S.perm.size();
+    const size_t byte0 = S.packed_bytes;
+    if ((byte0 + Q.packed_bytes) / 16 >= 0xffffffffull) return false;
+    for (Piece pc : Q.pieces) {
+      pc.data_off16 += (uint32_t)(byte0 / 16);
+      pc.perm_off += perm0;
+      S.pieces.push_back(pc);
+    }
+    for (int r : Q.perm) S.perm.push_back(r < 0 ? r : r + p * rows);          // global row id of the panel matrix
+    for (int w = 0; w < n * W; ++w)
+      S.warp_begin[(size_t)cta * W + w] = piece0 + (w <= Q.grid * W ? Q.warp_begin[std::min(w, Q.grid * W)] : (int)Q.pieces.size());
+    S.packed_bytes += Q.packed_bytes;
+    S.max_piece_bytes = std::max(S.max_piece_bytes, Q.max_piece_bytes);
+    S.sigma = std::max(S.sigma, Q.sigma);
+    cta += n;
+  }
+  S.warp_begin[(size_t)H.grid * W] = (int)S.pieces.size();
+  S.grid = H.grid;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // engine
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -269,6 +583,16 @@ struct DeviceCsr {
   int rows = 0, cols = 0, nnz = 0, grid = 0, npieces = 0, nlong = 0;
   int stage_bytes = 0, nstages = 2, smem_bytes = 0;
   size_t packed_bytes = 0;
+  // run layout (run_spmv.cuh): row-major chunk stream, natural row order
+  std::vector<int> h_rowptr;             // host copy of rowptr (plans; column counts of the transpose)
+  unsigned char* run_chunks = nullptr;
+  int *run_sptr = nullptr, *run_wcb = nullptr;
+  ChunkDesc* run_desc = nullptr;
+  int run_grid = 0, run_nchunks = 0, run_nstages = 2;
+  bool run_on = false;
+  RunView<T> run_view() const {
+    return RunView<T>{run_chunks, run_wcb, long_rows, nlong, rowptr, colidx, vals, partials, ticket, run_nstages, run_grid};
+  }
   SellView<T> view() const {
     return SellView<T>{packed, pieces, warp_begin, long_rows, nlong, rowptr, colidx, vals, partials, ticket,
                        stage_bytes, nstages, grid};
@@ -342,6 +666,19 @@ struct EngineT {
   bool check_warm[2][2] = {{false, false}, {false, false}};
   Scalars* h_scalars = nullptr;          // pinned read-back buffer
   std::vector<void*> allocs;
+  // layouts of the two iteration kernels.  k1 (K^T y): 0 = SELL (stream_spmv.cuh), 1 = run layout (run_spmv.cuh),
+  // 2 = shared-memory panels (panel_spmv.cuh; falls back to 0 when y does not fit).  k2 (K x): 0 = SELL, 1 = run.
+  int k1 = 0, k2 = 0;
+  struct Panel {
+    bool on = false;
+    int P = 0, panel_cap = 0, smem = 0, cgrid = 0;
+    DeviceCsr<T> M;                      // the panel matrix (P * n rows, panel-relative columns): CSR + SELL copy
+    int *cta_panel = nullptr, *panel_begin = nullptr;
+    T* partial = nullptr;                // P x n partial sums of K^T y
+    double* cpartials = nullptr;         // combine kernel: per-CTA reduction slots
+    unsigned int* cticket = nullptr;
+    PanelInfo info() const { return PanelInfo{cta_panel, panel_begin, panel_cap}; }
+  } panel;
 };
 
 // stream-ordered allocation from the device's default pool (kept cached: building an engine right after another
@@ -413,6 +750,100 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
   return cudaLaunchKernelEx(&cfg, stream_kernel<Op>, A.view(), op);
 }
 
+static inline int ew_blocks(int64_t len, int sms) {
+  int64_t b = (len + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sms * 8));
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per kernel AND device
+template <typename F>
+static cudaError_t ensure_smem_attr(F* func, int bytes) {
+  static std::mutex mu;
+  static unsigned long long done = 0;       // bit d: set for device d (this instantiation's kernel)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && (done >> dev) & 1ull) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+  return e;
+}
+
+static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, size_t smem, cudaStream_t st) {
+  cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
+constexpr int RUN_MAX_DYN_SMEM = 227 * 1024 - 4096;
+
+template <class Op>
+static cudaError_t prep_run_kernel() {
+  return ensure_smem_attr(run_kernel<Op>, RUN_MAX_DYN_SMEM);
+}
+
+template <class Op>
+static cudaError_t launch_run(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st) {
+  using T = typename Op::value_type;
+  cudaError_t e = prep_run_kernel<Op>();
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pdl_config(cfg, attr, A.run_grid, PDLP_RUN_W * 32, (size_t)RunSmem<T, uint32_t, Op::NV, PDLP_RUN_W>::total(A.run_nstages), st);
+  return cudaLaunchKernelEx(&cfg, run_kernel<Op>, A.run_view(), op);
+}
+
+// K^T y through the shared-memory panels, then the combine kernel with the op's row epilogue
+template <typename T, class Op>
+static cudaError_t launch_panel_combine(EngineT<T>* E, Op op, const T* in, cudaStream_t st) {
+  const auto& P = E->panel;
+  const int rows = (int)E->base->n;
+  cudaError_t e = ensure_smem_attr(panel_kernel<T>, RUN_MAX_DYN_SMEM);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pdl_config(cfg, attr, P.M.grid, StreamCfg<T>::NT, (size_t)P.smem, st);
+  e = cudaLaunchKernelEx(&cfg, panel_kernel<T>, P.M.view(), P.info(), in, P.partial, (const int*)&E->S->stop);
+  if (e != cudaSuccess) return e;
+  pdl_config(cfg, attr, P.cgrid, COMBINE_THREADS, 0, st);
+  return cudaLaunchKernelEx(&cfg, combine_kernel<Op>, (const T*)P.partial, P.P, rows, op, P.cpartials, P.cticket);
+}
+
+// fill the run-layout chunks / the panel matrix from the CSR master copy
+template <typename T>
+static int pack_run(EngineT<T>* E, DeviceCsr<T>& A) {
+  pdlp_engine* B = E->base;
+  if (!A.run_on || A.run_nchunks == 0) return 0;
+  run_pack_kernel<T><<<std::min(A.run_nchunks, B->sms * 32), RunCfg<T, uint32_t>::CHUNK, 0, B->stream>>>(
+      A.run_desc, A.run_nchunks, A.rows, A.run_sptr, A.rowptr, A.colidx, A.vals, A.run_chunks);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+static int pack_panels(EngineT<T>* E, bool with_columns) {
+  pdlp_engine* B = E->base;
+  auto& P = E->panel;
+  const DeviceCsr<T>& A = E->Kt;
+  if (!P.on) return 0;
+  panel_fill_kernel<T><<<ew_blocks(A.rows, B->sms), 256, 0, B->stream>>>(A.rowptr, A.colidx, A.vals, A.rows, P.panel_begin,
+                                                                        P.P, P.M.rowptr, with_columns ? P.M.colidx : nullptr,
+                                                                        P.M.vals);
+  CU(cudaGetLastError());
+  if (P.M.npieces > 0) {
+    pack_kernel<T><<<std::min(P.M.npieces, B->sms * 16), 256, 0, B->stream>>>(P.M.pieces, P.M.perm, P.M.npieces, P.M.rowptr,
+                                                                             P.M.colidx, P.M.vals, P.M.packed);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
 // (re)fill the packed copy from the CSR master copy (after create and after every scaling pass)
 template <typename T>
 static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
@@ -421,6 +852,117 @@ static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
   pack_kernel<T><<<std::min(A.npieces, B->sms * 16), 256, 0, B->stream>>>(A.pieces, A.perm, A.npieces, A.rowptr,
                                                                          A.colidx, A.vals, A.packed);
   CU(cudaGetLastError());
+  int rc = pack_run<T>(E, A);
+  if (rc) return rc;
+  if (&A == &E->Kt) return pack_panels<T>(E, false);
+  return 0;
+}
+
+// PDLP_LAYOUT selects the layout of the two iteration kernels when the engine is created:
+//   "sell"  (default) both kernels on SELL-32-sigma slices (stream_spmv.cuh)
+//   "run"   both on the row-major run layout (run_spmv.cuh)
+//   "panel" K^T y through shared-memory panels when y fits (panel_spmv.cuh), K x on SELL; "runpanel": panels + run
+// Measured on config 2 (round 2, us per launch K1 / K2): sell 35.8 / 37.0, run 45.2 / 45.1, panel 45.8 / 36.3 -- the
+// alternatives are parity-tested opt-ins, DESIGN.md section 4 explains what bounds each.
+static void layout_from_env(int* k1, int* k2) {
+  const char* v = getenv("PDLP_LAYOUT");
+  *k1 = 0; *k2 = 0;
+  if (!v || !*v || !strcmp(v, "auto") || !strcmp(v, "sell")) return;
+  if (!strcmp(v, "run")) { *k1 = 1; *k2 = 1; }
+  else if (!strcmp(v, "panel")) { *k1 = 2; *k2 = 0; }
+  else if (!strcmp(v, "runpanel")) { *k1 = 2; *k2 = 1; }
+}
+
+// run-layout copy of a matrix (plan on the host from the row lengths, packing on the device)
+template <typename T>
+static int build_run(EngineT<T>* E, DeviceCsr<T>& A) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  using Cfg = RunCfg<T, uint32_t>;
+  if ((unsigned)A.cols >= (unsigned)Cfg::END) return 0;             // column indices need the END bit
+  HostRun P = build_run_plan(A.h_rowptr.data(), A.rows, PDLP_LONG_ROW, B->sms, PDLP_RUN_W, Cfg::CHUNK);
+  if (!P.ok) return 0;                                              // falls back to SELL
+  A.run_grid = P.grid;
+  A.run_nchunks = (int)P.chunks.size();
+  A.run_nstages = std::max(2, std::min((int)PDLP_SMAX, (int)(PDLP_RUN_BUDGET / ((size_t)PDLP_RUN_W * Cfg::STAGE_BYTES))));
+  ALLOC(A.run_chunks, P.chunks.size() * Cfg::CHUNK_BYTES + 16);
+  ALLOC(A.run_sptr, P.sptr.size());
+  ALLOC(A.run_desc, P.chunks.size() + 1);
+  ALLOC(A.run_wcb, P.warp_chunk_begin.size());
+  CU(cudaMemcpyAsync(A.run_sptr, P.sptr.data(), sizeof(int) * P.sptr.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.run_desc, P.chunks.data(), sizeof(ChunkDesc) * P.chunks.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.run_wcb, P.warp_chunk_begin.data(), sizeof(int) * P.warp_chunk_begin.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));      // the host vectors go out of scope
+  if (P.grid > A.grid) {              // per-CTA reduction slots are shared with the SELL kernels
+    ALLOC(A.partials, (size_t)P.grid * MAX_RED);
+  }
+  A.run_on = true;
+  return pack_run<T>(E, A);
+}
+
+// K^T as shared-memory panels (only when the gathered vector is small enough and no row needs the CTA path)
+template <typename T>
+static int build_panels(EngineT<T>* E) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  DeviceCsr<T>& A = E->Kt;
+  using Cfg = StreamCfg<T>;
+  auto& D = E->panel;
+  const char* force = getenv("PDLP_PANEL_MIN_NNZ");
+  const long long min_nnz = force ? atoll(force) : 500000;
+  if (A.nlong > 0 || A.nnz < min_nnz || E->K.h_rowptr.empty()) return 0;
+  HostPanel H;
+  if (!panel_boundaries(E->K.h_rowptr.data(), A.cols, (int)sizeof(T), B->sms, H)) return 0;
+  ALLOC(D.panel_begin, H.panel_begin.size());
+  CU(cudaMemcpyAsync(D.panel_begin, H.panel_begin.data(), sizeof(int) * H.panel_begin.size(), cudaMemcpyHostToDevice, st));
+  int* d_cnt = nullptr;
+  ALLOC(d_cnt, (size_t)H.P * A.rows);
+  panel_count_kernel<<<ew_blocks(A.rows, B->sms), 256, 0, st>>>(A.rowptr, A.colidx, A.rows, D.panel_begin, H.P, d_cnt);
+  CU(cudaGetLastError());
+  std::vector<int> cnt((size_t)H.P * A.rows);
+  CU(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (!panel_plan(cnt.data(), A.rows, (int)sizeof(T), Cfg::W, Cfg::KB, H)) return 0;
+  const HostSell& S = H.sell;
+  // shared memory: the panel, then the rings (as many stages as fit)
+  const int panel_bytes = (int)(((size_t)H.panel_cap * sizeof(T) + 127) / 128 * 128);
+  DeviceCsr<T>& M = D.M;
+  M.rows = H.P * A.rows; M.cols = H.panel_cap; M.nnz = A.nnz;
+  M.stage_bytes = (S.max_piece_bytes + 127) / 128 * 128;
+  M.nstages = std::min((int)Cfg::SMAX, (RUN_MAX_DYN_SMEM - panel_bytes - 128) / (Cfg::W * M.stage_bytes));
+  if (M.nstages < 2) return 0;
+  M.grid = S.grid; M.npieces = (int)S.pieces.size(); M.nlong = 0; M.packed_bytes = S.packed_bytes;
+  D.P = H.P; D.panel_cap = H.panel_cap;
+  D.smem = panel_bytes + Cfg::W * M.nstages * M.stage_bytes + 128;
+  D.cgrid = std::max(1, std::min(B->sms * 8, (A.rows + COMBINE_THREADS - 1) / COMBINE_THREADS));
+  ALLOC(M.rowptr, H.rowptr.size());
+  ALLOC(M.colidx, (size_t)A.nnz + 1);
+  ALLOC(M.vals, (size_t)A.nnz + 1);
+  ALLOC(M.packed, S.packed_bytes + 16);
+  ALLOC(M.pieces, S.pieces.size() + 1);
+  ALLOC(M.perm, S.perm.size() + 32);
+  ALLOC(M.warp_begin, S.warp_begin.size());
+  ALLOC(M.long_rows, 1);
+  ALLOC(M.partials, (size_t)S.grid * MAX_RED);
+  ALLOC(M.ticket, 1);
+  ALLOC(D.cta_panel, H.cta_panel.size());
+  ALLOC(D.partial, (size_t)H.P * A.rows);
+  ALLOC(D.cpartials, (size_t)D.cgrid * MAX_RED);
+  ALLOC(D.cticket, 1);
+  CU(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned int), st));
+  CU(cudaMemsetAsync(D.cticket, 0, sizeof(unsigned int), st));
+  CU(cudaMemcpyAsync(M.rowptr, H.rowptr.data(), sizeof(int) * H.rowptr.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(M.pieces, S.pieces.data(), sizeof(Piece) * S.pieces.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(M.perm, S.perm.data(), sizeof(int) * S.perm.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(M.warp_begin, S.warp_begin.data(), sizeof(int) * S.warp_begin.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(D.cta_panel, H.cta_panel.data(), sizeof(int) * H.cta_panel.size(), cudaMemcpyHostToDevice, st));
+  D.on = true;
+  int rc = pack_panels<T>(E, true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));      // the host vectors go out of scope
+  if (getenv("PDLP_TRACE_SETUP"))
+    fprintf(stderr, "[pdlp setup] K^T panels: %d panels (cap %d elements), sigma %d, %d pieces, %.1f MB packed, %d ring stages of %d B, "
+            "%d B shared memory\n", D.P, D.panel_cap, S.sigma, M.npieces, S.packed_bytes / 1e6, M.nstages, M.stage_bytes, D.smem);
   return 0;
 }
 
@@ -450,7 +992,8 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   CU(cudaMemcpyAsync(A.rowptr, rowptr, sizeof(int) * (rows + 1), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(A.colidx, colidx, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(A.vals, vals, sizeof(T) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
-  std::vector<int> h_rowptr(rows + 1);
+  std::vector<int>& h_rowptr = A.h_rowptr;
+  h_rowptr.resize((size_t)rows + 1);
   CU(cudaMemcpyAsync(h_rowptr.data(), A.rowptr, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (h_rowptr[0] != 0 || h_rowptr[rows] != nnz) return fail(PDLP_ERR_INVALID, "rowptr does not span [0, nnz]");
@@ -458,7 +1001,7 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   tr.lap("csr copy + rowptr to host");
   using Cfg = StreamCfg<T>;
-  HostSell P = build_sell_plan(h_rowptr, rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
+  HostSell P = build_sell_plan(h_rowptr.data(), rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
                                E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
   tr.lap("plan (host)");
   // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows
@@ -490,11 +1033,6 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   return 0;
 }
 
-static inline int ew_blocks(int64_t len, int sms) {
-  int64_t b = (len + 255) / 256;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sms * 8));
-}
-
 template <typename T>
 static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
                          const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
@@ -510,9 +1048,28 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   if (rc) return rc;
   rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals);
   if (rc) return rc;
+  layout_from_env(&E->k1, &E->k2);
+  if (E->k2 == 1) {
+    rc = build_run<T>(E, E->K);
+    if (rc) return rc;
+    if (!E->K.run_on) E->k2 = 0;
+  }
+  if (E->k1 == 1) {
+    rc = build_run<T>(E, E->Kt);
+    if (rc) return rc;
+    if (!E->Kt.run_on) E->k1 = 0;
+  }
+  if (E->k1 == 1 || E->k2 == 1) tr.lap("run layout");
+  if (E->k1 == 2) {
+    rc = build_panels<T>(E);
+    if (rc) return rc;
+    if (!E->panel.on) E->k1 = 0;
+    tr.lap("K^T panels");
+  }
   ALLOC(E->c, n); ALLOC(E->l, n); ALLOC(E->u, n); ALLOC(E->q, m);
   ALLOC(E->xp, n); ALLOC(E->xsum, n); ALLOC(E->xlast, n); ALLOC(E->X4, n);
-  ALLOC(E->y, m); ALLOC(E->ysum, m); ALLOC(E->ylast, m); ALLOC(E->Y4, m);
+  ALLOC(E->y, m + 4);      // the panel kernel's bulk copies round the last panel up to 16 bytes
+  ALLOC(E->ysum, m); ALLOC(E->ylast, m); ALLOC(E->Y4, m);
   ALLOC(E->drow, m); ALLOC(E->dcol, n);
   ALLOC(E->tmp_n, n); ALLOC(E->tmp_n2, n); ALLOC(E->tmp_m, m);
   ALLOC(E->kty_old, n); ALLOC(E->lam_prev, n);
@@ -590,10 +1147,14 @@ static int refresh_norms(EngineT<T>* E) {
 template <typename T, bool SP, bool INF>
 static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
   PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
-  cudaError_t e = launch_stream(E->Kt, p, st, E->y, sizeof(T) * (size_t)E->base->m);
+  cudaError_t e;
+  if (E->k1 == 2) e = launch_panel_combine<T>(E, p, (const T*)E->y, st);
+  else if (E->k1 == 1) e = launch_run(E->Kt, p, st);
+  else e = launch_stream(E->Kt, p, st, E->y, sizeof(T) * (size_t)E->base->m);
   if (e != cudaSuccess) return e;
   DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-  e = launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
+  if (E->k2 == 1) e = launch_run(E->K, d, st);
+  else e = launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
   if (e != cudaSuccess) return e;
   if (INF) {
     InfeasColsOp<T> f{E->y, E->c, E->l, E->u, E->kty_old, E->lam_prev, E->S};
@@ -627,8 +1188,8 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   cudaStream_t st = B->stream;
   if (n_iters <= 0) return 0;
   if (save_prev) B->have_prev = true;
-  if (use_graph == 2 && !B->infeas) {
-    // one persistent cooperative kernel for the whole block
+  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0) {
+    // one persistent cooperative kernel for the whole block (SELL layout only; otherwise the CUDA graph below)
     const int grid = std::max(E->K.grid, E->Kt.grid);
     const int stages = std::min(E->K.nstages, E->Kt.nstages);
     const int stage_bytes = std::max(E->K.stage_bytes, E->Kt.stage_bytes);
@@ -670,6 +1231,17 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   CU((prep_kernel<DualOp<T, true, true>>()));
   CU((prep_kernel<DualOp<T, false, true>>()));
   CU((prep_kernel<InfeasColsOp<T>>()));
+  if (E->k1 || E->k2) {
+    CU((prep_run_kernel<PrimalOp<T, true, false>>()));
+    CU((prep_run_kernel<PrimalOp<T, false, false>>()));
+    CU((prep_run_kernel<PrimalOp<T, true, true>>()));
+    CU((prep_run_kernel<PrimalOp<T, false, true>>()));
+    CU((prep_run_kernel<DualOp<T, true, false>>()));
+    CU((prep_run_kernel<DualOp<T, false, false>>()));
+    CU((prep_run_kernel<DualOp<T, true, true>>()));
+    CU((prep_run_kernel<DualOp<T, false, true>>()));
+    CU(ensure_smem_attr(panel_kernel<T>, RUN_MAX_DYN_SMEM));
+  }
   CU(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = enqueue_iterations<T>(E, n_iters, save_prev, cap);
   cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
@@ -696,9 +1268,12 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
     PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
     DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
     CU(cudaEventRecord(ev[3 * i], st));
-    CU(launch_stream(E->Kt, p, st));
+    if (E->k1 == 2) CU(launch_panel_combine<T>(E, p, (const T*)E->y, st));
+    else if (E->k1 == 1) CU(launch_run(E->Kt, p, st));
+    else CU(launch_stream(E->Kt, p, st));
     CU(cudaEventRecord(ev[3 * i + 1], st));
-    CU(launch_stream(E->K, d, st));
+    if (E->k2 == 1) CU(launch_run(E->K, d, st));
+    else CU(launch_stream(E->K, d, st));
     CU(cudaEventRecord(ev[3 * i + 2], st));
   }
   CU(cudaStreamSynchronize(st));
@@ -1388,7 +1963,7 @@ extern "C" int pdlp_plan_inspect(const int32_t* host_rowptr, int64_t rows, int32
   for (int64_t r = 0; r < rows; ++r)
     if (rowptr[r + 1] < rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   const int W = PDLP_W, KB = PDLP_KB;
-  HostSell P = build_sell_plan(rowptr, (int)rows, value_bytes, W, KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
+  HostSell P = build_sell_plan(rowptr.data(), (int)rows, value_bytes, W, KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
                                sms * PDLP_CTAS * PDLP_OVERSUB);
   memset(o, 0, sizeof(*o));
   o->rows = rows;
@@ -1450,6 +2025,189 @@ extern "C" int pdlp_plan_inspect(const int32_t* host_rowptr, int64_t rows, int32
   o->ranges_ok = rok ? 1 : 0;
   o->max_warp_bytes = maxb;
   o->mean_warp_bytes = o->warps ? sumb / o->warps : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Host-side checker of the run layout (tests/test_cpu_plan.py): plans and packs a CSR matrix with the SAME planner and
+// per-slot packer the device path uses, then walks the chunks with a 32-lane emulation of run_phase (ballots, slots,
+// segmented carry scan, staging rounds) and returns out = A x.  mode 0: plain layout (rows above long_row are summed
+// directly, as long_rows_phase does); mode 1: shared-memory panels + combine.  No GPU involved.
+// ---------------------------------------------------------------------------
+template <typename CT>
+static void emulate_walk(const unsigned char* chunks, int cb, int ce, const double* operand, double* out, int cap,
+                         int64_t* rows_done) {
+  using Cfg = RunCfg<double, CT>;
+  constexpr int E = Cfg::E;
+  double carry = 0.0;
+  std::vector<double> stg(cap);
+  for (int c = cb; c < ce; ++c) {
+    const unsigned char* st = chunks + (size_t)c * Cfg::CHUNK_BYTES;
+    const double* vals = reinterpret_cast<const double*>(st);
+    const CT* cols = reinterpret_cast<const CT*>(st + Cfg::VALS_BYTES);
+    const unsigned* meta = reinterpret_cast<const unsigned*>(st + Cfg::VALS_BYTES + Cfg::COLS_BYTES);
+    const RunTrailer tr = *reinterpret_cast<const RunTrailer*>(st + Cfg::VALS_BYTES + Cfg::COLS_BYTES + Cfg::META_BYTES);
+    const int nrows = tr.nrows;
+    double g[32][E];
+    for (int lane = 0; lane < 32; ++lane)
+      for (int k = 0; k < E; ++k) g[lane][k] = operand[(int)(cols[k * 32 + lane] & Cfg::MASK)];
+    double cin[32], tail[32];
+    for (int lo = 0; lo == 0 || lo < nrows; lo += cap) {
+      for (int lane = 0; lane < 32; ++lane) {
+        const unsigned endm = meta[lane] & 0xffu;
+        double acc = 0.0;
+        int slot = (int)((meta[lane] >> 8) & 0x1ffu) - lo;
+        for (int k = 0; k < E; ++k) {
+          acc += vals[k * 32 + lane] * g[lane][k];
+          if ((tr.any_steps >> k) & 1u) {
+            if ((endm >> k) & 1u) {
+              if ((unsigned)slot < (unsigned)cap) stg[slot] = acc;
+              ++slot;
+              acc = 0.0;
+            }
+          }
+        }
+        tail[lane] = acc;
+      }
+      if (lo == 0) {
+        const unsigned F = tr.end_lanes;
+        double sv[32];
+        for (int lane = 0; lane < 32; ++lane) sv[lane] = (lane == 0 && !(meta[0] & 0xffu)) ? carry + tail[0] : tail[lane];
+        for (int d = 1; d < 32; d <<= 1) {
+          double nv[32];
+          for (int lane = 0; lane < 32; ++lane) {
+            const unsigned wm = ((1u << d) - 1u) << ((lane - d + 1) & 31);
+            const bool take = lane >= d && !(F & wm);
+            nv[lane] = take ? sv[lane - d] + sv[lane] : sv[lane];
+          }
+          for (int lane = 0; lane < 32; ++lane) sv[lane] = nv[lane];
+        }
+        for (int lane = 0; lane < 32; ++lane) cin[lane] = lane == 0 ? carry : sv[lane - 1];
+        carry = sv[31];
+      }
+      for (int lane = 0; lane < 32; ++lane) {
+        const int first = (int)((meta[lane] >> 8) & 0x1ffu) - lo;
+        if ((meta[lane] & 0xffu) && (unsigned)first < (unsigned)cap) stg[first] = cin[lane] + stg[first];
+      }
+      const int cnt = std::min(cap, nrows - lo);
+      for (int i = 0; i < cnt; ++i) {
+        out[tr.row0 + lo + i] = stg[i];
+        ++*rows_done;
+      }
+    }
+  }
+}
+
+extern "C" int pdlp_run_emulate(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t rows,
+                                int64_t cols, int32_t sms, int32_t long_row, int32_t mode, const double* x, double* out,
+                                pdlp_run_info* info) {
+  if (!rowptr || !x || !out || !info || rows < 1 || cols < 1 || sms < 1 || rows > 0x7ffffff0 || cols > 0x3ffffff0)
+    return fail(PDLP_ERR_INVALID, "bad argument");
+  memset(info, 0, sizeof(*info));
+  const int R = (int)rows;
+  int64_t rows_done = 0;
+  for (int r = 0; r < R; ++r) out[r] = NAN;
+  if (mode == 0) {
+    using Cfg = RunCfg<double, uint32_t>;
+    HostRun P = build_run_plan(rowptr, R, long_row, sms, PDLP_RUN_W, Cfg::CHUNK);
+    if (!P.ok) return fail(PDLP_ERR_INVALID, "stream too long");
+    const int nchunks = (int)P.chunks.size();
+    std::vector<unsigned char> chunks((size_t)nchunks * Cfg::CHUNK_BYTES + 16, 0xcd);
+    const int nw = P.grid * PDLP_RUN_W;
+    for (int c = 0; c < nchunks; ++c) {
+      unsigned char* blk = chunks.data() + (size_t)c * Cfg::CHUNK_BYTES;
+      unsigned char ends[Cfg::CHUNK];
+      int row0 = -1;
+      for (int s = 0; s < Cfg::CHUNK; ++s) {
+        int row;
+        ends[s] = run_pack_slot<double, uint32_t>(P.chunks[c], s, R, P.sptr.data(), rowptr, colidx, vals, blk, &row) ? 1 : 0;
+        if (s == 0) row0 = row;
+      }
+      run_pack_meta_host<Cfg::E>(ends, row0, reinterpret_cast<unsigned*>(blk + Cfg::VALS_BYTES + Cfg::COLS_BYTES),
+                                 reinterpret_cast<RunTrailer*>(blk + Cfg::VALS_BYTES + Cfg::COLS_BYTES + Cfg::META_BYTES));
+    }
+    for (int w = 0; w < nw; ++w)
+      emulate_walk<uint32_t>(chunks.data(), P.warp_chunk_begin[w], P.warp_chunk_begin[w + 1], x, out, Cfg::CAP, &rows_done);
+    for (int r : P.long_rows) {
+      double a = 0.0;
+      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) a += vals[e] * x[colidx[e]];
+      out[r] = a;
+      ++rows_done;
+    }
+    info->grid = P.grid; info->warps = nw; info->chunks = nchunks; info->long_rows = (int32_t)P.long_rows.size();
+    info->stream_entries = P.sptr[R];
+    info->chunk_bytes = Cfg::CHUNK_BYTES;
+    int64_t mx = 0;
+    for (int w = 0; w < nw; ++w) mx = std::max<int64_t>(mx, P.warp_chunk_begin[w + 1] - P.warp_chunk_begin[w]);
+    info->max_warp_chunks = (int32_t)mx;
+  } else {
+    // nonzeros per column (= per element of the gathered vector)
+    std::vector<int> cpre((size_t)cols + 1, 0);
+    for (int e = rowptr[0]; e < rowptr[R]; ++e) ++cpre[(size_t)colidx[e] + 1];
+    for (int64_t j = 0; j < cols; ++j) cpre[j + 1] += cpre[j];
+    HostPanel H;
+    if (!panel_boundaries(cpre.data(), (int)cols, 8, sms, H)) return fail(PDLP_ERR_INVALID, "the vector does not fit the panels");
+    std::vector<int> cnt((size_t)H.P * R, 0);
+    for (int r = 0; r < R; ++r)
+      for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
+        for (int p = 0; p < H.P; ++p)
+          if (colidx[e] >= H.panel_begin[p] && colidx[e] < H.panel_begin[p + 1]) ++cnt[(size_t)p * R + r];
+    if (!panel_plan(cnt.data(), R, 8, PDLP_W, PDLP_KB, H)) return fail(PDLP_ERR_INVALID, "a row part needs the CTA path");
+    // the panel matrix on the host (what panel_fill_kernel writes)
+    std::vector<int> pcol((size_t)rowptr[R] - rowptr[0]);
+    std::vector<double> pval(pcol.size());
+    {
+      std::vector<int> cur(H.rowptr.begin(), H.rowptr.end() - 1);
+      for (int r = 0; r < R; ++r)
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e)
+          for (int p = 0; p < H.P; ++p)
+            if (colidx[e] >= H.panel_begin[p] && colidx[e] < H.panel_begin[p + 1]) {
+              int& c = cur[(size_t)p * R + r];
+              pcol[c] = colidx[e] - H.panel_begin[p];
+              pval[c] = vals[e];
+              ++c;
+            }
+    }
+    // walk the plan the way the kernel's CTAs do: CTA b serves panel cta_panel[b] and must only meet rows of it
+    const HostSell& S = H.sell;
+    std::vector<double> partial((size_t)H.P * R, NAN);
+    std::vector<int> seen((size_t)H.P * R, 0);
+    bool ok = (int)S.warp_begin.size() == H.grid * PDLP_W + 1;
+    for (int b = 0; ok && b < H.grid; ++b) {
+      const int p = H.cta_panel[b];
+      for (int pc = S.warp_begin[(size_t)b * PDLP_W]; pc < S.warp_begin[(size_t)(b + 1) * PDLP_W]; ++pc) {
+        const Piece& d = S.pieces[pc];
+        if (!(d.flags & PIECE_FIRST)) continue;
+        for (int i = 0; i < (int)d.nslices * 32; ++i) {
+          const int row = S.perm[(size_t)d.perm_off + i];
+          if (row < 0 || ((d.flags & PIECE_WARP_ROW) && i > 0)) continue;
+          if (row / R != p) { ok = false; continue; }
+          ++seen[row];
+          double a = 0.0;
+          for (int e = H.rowptr[row]; e < H.rowptr[row + 1]; ++e) a += pval[e] * x[H.panel_begin[p] + pcol[e]];
+          partial[row] = a;
+        }
+      }
+    }
+    for (size_t i = 0; i < seen.size(); ++i) {
+      if (seen[i] != 1) ok = false;
+      else ++rows_done;
+    }
+    if (!ok) return fail(PDLP_ERR_STATE, "panel plan does not cover every (panel, row) exactly once inside its panel's CTAs");
+    for (int r = 0; r < R; ++r) {
+      double a = partial[r];
+      for (int p = 1; p < H.P; ++p) a += partial[(size_t)p * R + r];
+      out[r] = a;
+    }
+    rows_done /= H.P;
+    info->grid = H.grid; info->warps = H.grid * PDLP_W; info->chunks = (int32_t)S.pieces.size(); info->panels = H.P;
+    info->panel_cap = H.panel_cap;
+    info->stream_entries = 0;
+    for (const Piece& d : S.pieces) info->stream_entries += (int64_t)d.klen * d.nslices * 32;     // padded slots
+    info->chunk_bytes = S.max_piece_bytes;
+    info->max_warp_chunks = S.sigma;
+  }
+  info->rows_finished = rows_done;
   return 0;
 }
 

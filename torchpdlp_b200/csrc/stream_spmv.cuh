@@ -46,6 +46,9 @@ namespace pdlp {
 #ifndef PDLP_MINB
 #define PDLP_MINB 1       // CTAs per SM the register budget is sized for
 #endif
+#ifndef PDLP_PREFETCH
+#define PDLP_PREFETCH 0   // pieces a warp prefetches into L2 ahead of its ring (0 = off): the ring's bulk copies then hit
+#endif                    // L2, so the bytes in flight towards HBM are no longer bounded by the ring's shared memory
 #ifndef PDLP_SIGMA
 #define PDLP_SIGMA 128    // smallest sorting window (rows) the planner considers
 #endif
@@ -159,6 +162,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 #endif
 }
 
+// HBM -> L2 only: no shared memory, no completion to wait for
+__device__ __forceinline__ void prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ T shfl_xor_t(T v, int mask) {
   return __shfl_xor_sync(0xffffffffu, v, mask);
@@ -208,6 +216,73 @@ __device__ __forceinline__ void ring_prologue(const SellView<T>& A, const Ring& 
       mbar_arrive_expect_tx(&R.bars[s], bytes);
       tma_load_1d(R.mem + (size_t)s * R.stage_bytes, A.packed + (size_t)d.data_off16 * 16u, bytes, &R.bars[s]);
     }
+    if (PDLP_PREFETCH > 0 && pb + R.S < pe) {     // pieces are contiguous in memory: one prefetch for the next few
+      const int last = min(pe, pb + R.S + PDLP_PREFETCH) - 1;
+      const Piece d0 = A.pieces[pb + R.S], d1 = A.pieces[last];
+      const unsigned char* p0 = A.packed + (size_t)d0.data_off16 * 16u;
+      const unsigned char* p1 = A.packed + (size_t)d1.data_off16 * 16u + piece_bytes<T>(d1);
+      prefetch_l2(p0, (uint32_t)(p1 - p0));
+    }
+  }
+}
+
+// Rows too long for the streaming layouts: one row per CTA, straight from the CSR arrays, U independent gathers per
+// thread and batch; the row epilogue runs on thread 0.  s_red: W x SR doubles of shared scratch.
+template <class Op, int SR>
+__device__ __forceinline__ void long_rows_phase(const int* long_rows, int n_long, const int* rowptr, const int* colidx,
+                                                const typename Op::value_type* vals, Op& op,
+                                                double (&red)[Op::NRED > 0 ? Op::NRED : 1], double (*s_red)[SR]) {
+  using T = typename Op::value_type;
+  using Cfg = StreamCfg<T>;
+  constexpr int NV = Op::NV;
+  constexpr int U = (Cfg::U / Op::UDIV) > 0 ? (Cfg::U / Op::UDIV) : 1;
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const int nwarps = nthr >> 5;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int row = long_rows[li];
+    const int b = rowptr[row], e = rowptr[row + 1];
+    T acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = T(0);
+    for (int i = b + tid; i < e; i += U * nthr) {       // U independent gathers per thread and batch
+      typename Op::Gather g[U];
+      T a[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int idx = i + j * nthr;
+        if (idx < e) {
+          g[j] = op.gather(PDLP_COL(colidx[idx]));
+          a[j] = vals[idx];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (i + j * nthr < e) op.mac(acc, a[j], g[j]);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
+    }
+    __syncthreads();      // s_red free
+    if (lane == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s_red[warp][v] = (double)acc[v];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      T tot[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += s_red[w][v];
+        tot[v] = (T)t;
+      }
+      op.row_finish(row, op.row_load(row), tot, red);
+    }
   }
 }
 
@@ -222,55 +297,10 @@ __device__ __forceinline__ void stream_phase(const SellView<typename Op::value_t
   constexpr int NV = Op::NV;
   constexpr int U = (Cfg::U / Op::UDIV) > 0 ? (Cfg::U / Op::UDIV) : 1;
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
   const int lane = tid & 31;
 
   // ---------------- long rows: one row per CTA, straight from CSR ----------------
-  if (A.n_long > 0) {
-    for (int li = blockIdx.x; li < A.n_long; li += gridDim.x) {
-      const int row = A.long_rows[li];
-      const int b = A.rowptr[row], e = A.rowptr[row + 1];
-      T acc[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) acc[v] = T(0);
-      for (int i = b + tid; i < e; i += U * Cfg::NT) {       // U independent gathers per thread and batch
-        typename Op::Gather g[U];
-        T a[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const int idx = i + j * Cfg::NT;
-          if (idx < e) {
-            g[j] = op.gather(PDLP_COL(A.colidx[idx]));
-            a[j] = A.vals[idx];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          if (i + j * Cfg::NT < e) op.mac(acc, a[j], g[j]);
-      }
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[v] += shfl_xor_t(acc[v], o);
-      }
-      __syncthreads();      // s_red free
-      if (lane == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) s_red[warp][v] = (double)acc[v];
-      }
-      __syncthreads();
-      if (tid == 0) {
-        T tot[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          double t = 0.0;
-          for (int w = 0; w < Cfg::W; ++w) t += s_red[w][v];
-          tot[v] = (T)t;
-        }
-        op.row_finish(row, op.row_load(row), tot, red);
-      }
-    }
-  }
+  if (A.n_long > 0) long_rows_phase<Op, SR>(A.long_rows, A.n_long, A.rowptr, A.colidx, A.vals, op, red, s_red);
 
   // ---------------- SELL pieces: one row per lane ----------------
   // Software pipeline: while piece p is multiplied, reduced into its row and finished, the first batch of
@@ -299,9 +329,11 @@ __device__ __forceinline__ void stream_phase(const SellView<typename Op::value_t
   if (PIPE && pb < pe) issue_first(pb, g_cur);
   for (int p = pb; p < pe; ++p) {
     if (!PIPE) issue_first(p, g_cur);
-    Piece d_refill = Piece{0, 0, 0, 0, 0};
+    Piece d_refill = Piece{0, 0, 0, 0, 0}, d_pref = Piece{0, 0, 0, 0, 0};
     const bool refill = (p + R.S < pe);
+    const bool pref = PDLP_PREFETCH > 0 && (p + R.S + PDLP_PREFETCH < pe);
     if (refill && lane == 0) d_refill = A.pieces[p + R.S];        // used after this piece: latency hidden
+    if (pref && lane == 0) d_pref = A.pieces[p + R.S + PDLP_PREFETCH];
     const int s = R.stage(base + (unsigned)(p - pb));
     const unsigned char* st = stage_of(p);
     const Piece d = *reinterpret_cast<const Piece*>(st);          // stage already waited for by issue_first
@@ -371,6 +403,7 @@ __device__ __forceinline__ void stream_phase(const SellView<typename Op::value_t
       mbar_arrive_expect_tx(&R.bars[s], bytes);
       tma_load_1d(R.mem + (size_t)s * R.stage_bytes, A.packed + (size_t)d_refill.data_off16 * 16u, bytes, &R.bars[s]);
     }
+    if (pref && lane == 0) prefetch_l2(A.packed + (size_t)d_pref.data_off16 * 16u, piece_bytes<T>(d_pref));
     if constexpr (PIPE) {
 #pragma unroll
       for (int j = 0; j < U; ++j) g_cur[j] = g_nxt[j];

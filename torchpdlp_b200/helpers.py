@@ -1,6 +1,8 @@
 """Drop-in for torchPDLP's PDLP/helpers.py (norm / KKT / residual helpers)."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _cache
@@ -22,27 +24,29 @@ def _bounds_from_dual(l_dual, u_dual, is_neg_inf, is_pos_inf):
     return l, u
 
 
-_bound_cache = {}
+_bound_cache = []          # [(weakref l_dual, version, weakref u_dual, version, (l, u))]: see _cache for the rationale
 
 
 def _engine(K, m_ineq, c, q, l_dual, u_dual, is_neg_inf, is_pos_inf):
-    key = (l_dual.data_ptr(), u_dual.data_ptr())
-    lu = _bound_cache.get(key)
+    lu = None
+    for ent in list(_bound_cache):
+        a, va, b, vb, val = ent
+        if a() is None or b() is None:
+            _bound_cache.remove(ent)
+        elif a() is l_dual and b() is u_dual and va == l_dual._version and vb == u_dual._version:
+            lu = val
     if lu is None:
-        if len(_bound_cache) > 8:
-            _bound_cache.clear()
         lu = _bounds_from_dual(l_dual, u_dual, is_neg_inf, is_pos_inf)
-        _bound_cache[key] = lu
+        _bound_cache.append((weakref.ref(l_dual), l_dual._version, weakref.ref(u_dual), u_dual._version, lu))
+        del _bound_cache[:-8]
     return _cache.engine_for(K, m_ineq, c, q, lu[0], lu[1])
 
 
 def spectral_norm_estimate_torch(K, num_iters=10):
     """helpers.py:41-51.  Start vector: torch.randn(n, 1) from the global CPU
     generator in K's dtype."""
-    n = K.shape[1]
-    zeros_n = torch.zeros(n, dtype=K.dtype)
-    eng = _cache.engine_for(K, 0, zeros_n, torch.zeros(K.shape[0], dtype=K.dtype), zeros_n, zeros_n)
-    b0 = torch.randn(n, 1, dtype=K.dtype)
+    eng = _cache.engine_for_matrix(K)
+    b0 = torch.randn(K.shape[1], 1, dtype=K.dtype)
     return torch.tensor(eng.power_iteration(b0, num_iters), dtype=K.dtype, device=eng.device)
 
 

@@ -68,11 +68,13 @@ def run_restart_loop(engine: Engine, max_kkt, restart_period, time_limit, time_u
         restarted = False
         timed_out = False
         while j < max_kkt:
-            if time.time() - t_start + time_used >= time_limit:           # :68-74 (tested per block here)
+            timed_out = time.time() - t_start + time_used >= time_limit   # :68-74 (tested per block here)
+            if hasattr(engine, "agree_timeout"):                           # row-partitioned: one decision for all ranks
+                timed_out = engine.agree_timeout(timed_out)
+            if timed_out:
                 status = "Unsolved (Time limit exceeded)"
                 if verbose:
                     print("Time limit exceeded")
-                timed_out = True
                 break
             want = restart_period - (t % restart_period)
             iters, jj, kk = 0, j, k
@@ -172,3 +174,40 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
                 "bytes_per_iteration": engine.bytes_per_iteration}
         return x.reshape(-1, 1), prim_obj, k, n, j, status, total, info
     return x.reshape(-1, 1), prim_obj, k, n, j, status, total
+
+
+def pdlp_solver(mps_file_path, tol=1e-4, restart_period=40, verbose=True, max_iter=1000000, precondition=True,
+                adaptive_step=True, primal_update=True):
+    """The one-call entry on an MPS file of the reference's older line
+    (Packages/PDLP_without_presolve_infeasibility.py:747-789): same arguments, same defaults, same 5-tuple
+    ``(minimizer, objective_value, total_iterations, total_restarts, kkt_passes)``.  ``max_iter`` bounds the KKT
+    passes j, as there (its loops test ``j < max_iter``).  As in that file the minimizer is returned in the
+    ORIGINAL variables (its ``x / D_col`` at :745 undoes the scaling; here ``D_col * x_scaled``,
+    PDLP/primal_dual_hybrid_gradient.py:161), an (n, 1) tensor on the GPU.  Preconditioning is Ruiz
+    (enhancements.py:4-71).  A file that cannot be read raises (the reference prints and calls exit(1))."""
+    from .enhancements import ruiz_precondition
+    from .util import mps_to_standard_form
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("torchpdlp_b200 runs on a CUDA device (B200) only: no CPU fallback")
+    device = torch.device("cuda")
+    if verbose:
+        print(f"PyTorch is using ROCm/CUDA device: {torch.cuda.get_device_name(0)}")
+    c, K, q, m_ineq, l, u = mps_to_standard_form(mps_file_path, device=device, verbose=verbose)
+    time_used, data_precond, D_col = 0.0, None, None
+    if precondition:
+        K, c, q, l, u, data_precond, time_used = ruiz_precondition(c, K, q, l, u, device=device)
+        D_col = data_precond[0]
+    x, objective_value, k, n, j, status, _ = pdlp_algorithm(
+        K, m_ineq, c, q, l, u, device, max_kkt=max_iter, tol=tol, verbose=verbose, restart_period=restart_period,
+        precondition=precondition, primal_update=primal_update, adaptive=adaptive_step, data_precond=data_precond,
+        time_used=time_used)
+    minimizer = x * D_col.to(x.device).reshape(-1, 1) if D_col is not None else x
+    if verbose:
+        print("Objective Value:", objective_value)
+        print("Iterations:", k)
+        print("Restarts:", n)
+        print("KKT Passes:", j)
+        print("\nMinimizer (first 10 variables):")
+        print(minimizer[:10].cpu().numpy())
+    return minimizer, objective_value, k, n, j

@@ -288,6 +288,18 @@ class ShardedSolver:
     def state(self):
         return self.p.state()
 
+    def agree_timeout(self, timed_out: bool) -> bool:
+        """The wall-clock test of the restart loop (primal_dual_hybrid_gradient.py:68-74) is the only loop decision
+        taken from rank-local data: the ranks' clocks differ, and a rank that stopped alone would leave the others
+        waiting in the next exchange.  So the limit is reached when ANY rank has reached it (a sum over ranks of
+        the 0/1 flags, through the same exchange as every other collective), and all ranks stop in the same
+        block."""
+        if self.world <= 1 and not self._p2p_ready:
+            return bool(timed_out)
+        t = torch.tensor([1.0 if timed_out else 0.0], dtype=torch.float64, device=self.buf.device)
+        self._allreduce(t)
+        return bool(float(t.item()) > 0.5)
+
     def close(self):
         """Drop the captured graphs (they hold NCCL work) and the engine; call before destroy_process_group."""
         self._graphs.clear()

@@ -226,3 +226,26 @@ CONFIGS = {
 
 def make(name: str, **kw) -> SyntheticLP:
     return CONFIGS[name](**kw)
+
+
+def isolated_infeasible_lp(m_ineq=80_000, m_eq=20_000, n=200_000, nnz_per_row=50, seed=0, beta=5.0, delta=6.0,
+                           name="cfg3_isolated"):
+    """Config 3, the variant whose certificate the reference's heuristic reaches at full size: the config-2 LP with
+    variable 0 taken out of every row, cost 0, bounds [-10, 10], and a contradictory pair of ">=" rows on it alone,
+    x_0 >= beta and -x_0 >= -beta + delta (x_0 <= beta - delta < beta).  The infeasible part is decoupled from the
+    rest, so the differences of the iterates (what enhancements.py:106-161 tests) settle as fast as config 2
+    converges; y = e_1 + e_2 is a Farkas certificate (K^T y = 0, q^T y = delta > 0) and the violation delta / 2 per
+    row is far above the termination tolerance 1e-4 (1 + ||q||)."""
+    base = uniform_rows_lp(m_ineq, m_eq, n, nnz_per_row, seed, name)
+    K = base.K.tocsc(copy=True)
+    K.data[K.indptr[0]:K.indptr[1]] = 0.0
+    K = sp.csr_matrix(K.tocsr())
+    K.eliminate_zeros()
+    pair = sp.csr_matrix((np.array([1.0, -1.0]), (np.array([0, 1]), np.array([0, 0]))), shape=(2, n))
+    K = sp.vstack([pair, K], format="csr")
+    K.sort_indices()
+    K = sp.csr_matrix((K.data, K.indices.astype(np.int32), K.indptr.astype(np.int32)), shape=K.shape)
+    q = np.concatenate([[beta, -beta + delta], base.q])
+    c, l, u = base.c.copy(), base.l.copy(), base.u.copy()
+    c[0], l[0], u[0] = 0.0, -10.0, 10.0
+    return SyntheticLP(name, K, c, q, l, u, base.m_ineq + 2)
