@@ -128,6 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1: use the host's cores anyway
     lp = make_lp()
     st = OracleStepper(lp, "coo")
     t_iter = st.run(1)
@@ -402,6 +403,16 @@ def run_sharded(args, world, rank, local, dev):
     note(f"e2e done {status} k={k}")
     barrier()
     e2e_s = time.perf_counter() - t0
+    # ---- parity of the row-partitioned engine on this hardware (fails the run when it does not hold) ----
+    parity = sharded_parity(world, rank, dev, exchange, x)
+    # ---- config 5: the 500M-nnz LP, strong scaling over the same GPUs ----
+    cfg5 = None
+    if os.environ.get("PDLP_BENCH_CFG5", "1") != "0":
+        solver.close()
+        solver2.close()
+        solver = solver2 = None
+        torch.cuda.empty_cache()
+        cfg5 = run_cfg5(world, rank, dev, note)
     if rank == 0:
         peak, peak_src = measured_peak()
         b_iter_rank = 24 * Kb.nnz + 4 * (m_blk + n + 2) + 72 * n + 48 * m_blk
@@ -415,6 +426,10 @@ def run_sharded(args, world, rank, local, dev):
                            "allreduce of n+4 doubles per iteration inside the iteration kernels (peer memory over NVLink, "
                            "LL protocol)" if exchange == "p2p" else "1 NCCL allreduce of n+4 doubles per iteration"),
                        "exchange": exchange, "value_is": "n_gpus x iterations/s",
+                       "note": "weak scaling: the LP grows with N (one row block per GPU), so lines of different N are rates "
+                               "on different LPs (and not comparable with the cfg2 CPU arm); with exchange=p2p NCCL is only "
+                               "the control plane (handles, barriers), the data plane is peer memory over NVLink; the strong-"
+                               "scaling result on the fixed 500M-nnz LP is the cfg5 record",
                        "l2": "per-GPU working set ~140 MB > 126 MB L2; no explicit flush"},
             "us_per_iteration": 1e3 * ms / iters,
             "iteration_roofline_frac": b_iter_rank / (ms * 1e-3 / iters) / 1e9 / peak,
@@ -427,14 +442,162 @@ def run_sharded(args, world, rank, local, dev):
                          b_iter_rank / (ms * 1e-3 / iters) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b_iter_rank / (ms * 1e-3 / iters) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
             "cpu_baseline": None,
+            "parity": parity,
+            "cfg5": cfg5,
         }
         print(json.dumps(out), flush=True)
     # captured graphs hold NCCL work: drop them (and the engines) before the communicator goes away
-    solver.close()
-    solver2.close()
+    if solver is not None:
+        solver.close()
+        solver2.close()
     torch.cuda.synchronize(dev)
     dist.barrier()
     dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.exit(3)
+
+
+def sharded_parity(world, rank, dev, exchange, x_replica):
+    """Hardware parity of the row-partitioned engine: (1) the replicas of x of the solve just done are bit-identical
+    on all ranks; (2) config 2 (the real 100k x 200k LP) cut into `world` row blocks gives the same solve as the
+    single-GPU engine on the whole LP: fixed step -> equal k / n / j, objective to 1e-9; adaptive -> equal status and
+    n, k within one restart period, objective to 1e-6 (the bands of tests/test_gpu_solve.py)."""
+    import torch.distributed as dist
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.engine import Engine
+    from torchpdlp_b200.primal_dual_hybrid_gradient import initial_step
+    from torchpdlp_b200.sharded import build_rank_engine, partition_rows
+    lo, hi = x_replica.clone(), x_replica.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool(torch.equal(lo, hi))
+    lp = synthetic.uniform_rows_lp()
+    cuts = partition_rows(lp.K.indptr, world)
+    r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+    mi = min(max(lp.m_ineq - r0, 0), r1 - r0)
+    Kb = lp.K[r0:r1].tocsr()
+    Kb.sort_indices()
+    runs = []
+    ok = identical
+    for adaptive, pw in ((False, False), (True, True)):
+        solver = build_rank_engine(Kb, mi, lp.c, lp.q[r0:r1], lp.l, lp.u, device=dev, exchange=exchange)
+        torch.manual_seed(0)
+        xs, ys, obj, k, nres, j, status, secs, sig = solver.solve(adaptive=adaptive, primal_update=pw, max_kkt=20_000)
+        a, b = xs.clone(), xs.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MIN)
+        dist.all_reduce(b, op=dist.ReduceOp.MAX)
+        same_x = bool(torch.equal(a, b))
+        solver.close()
+        rec = {"adaptive": adaptive, "sharded": {"status": status, "k": int(k), "n": int(nres), "j": int(j), "obj": obj},
+               "x_replicas_bit_identical": same_x}
+        good = torch.zeros(1, device=dev)
+        if rank == 0:                                   # the single-GPU engine on the whole LP
+            eng = Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u, device=dev)
+            torch.manual_seed(0)
+            eta, omega, sigma = initial_step(eng, 100)
+            eng.set_iterate(None, None); eng.set_counters(0, 0); eng.set_step(eta, omega, 1.0, adaptive)
+            eng.set_options(1e-4, pw, False, 1e-4)
+            ref = eng.solve(20_000, RESTART_PERIOD, 3600.0, 0.0, True)
+            eng.close()
+            rec["single_gpu"] = {"status": ref.status, "k": int(ref.k), "n": int(ref.n), "j": int(ref.j), "obj": ref.prim_obj}
+            rel = abs(obj - ref.prim_obj) / max(1.0, abs(ref.prim_obj))
+            if adaptive:
+                match = status == ref.status and nres == ref.n and abs(k - ref.k) <= RESTART_PERIOD and rel < 1e-6
+            else:
+                match = status == ref.status and (k, nres, j) == (ref.k, ref.n, ref.j) and rel < 1e-9
+            rec["rel_obj_diff"] = rel
+            rec["match"] = bool(match and same_x)
+            good[0] = 1.0 if rec["match"] else 0.0
+        dist.broadcast(good, src=0)
+        ok = ok and bool(good.item() > 0.5)
+        runs.append(rec)
+    return {"ok": bool(ok), "x_replicas_bit_identical": identical, "cfg2_vs_single_gpu": runs}
+
+
+def run_cfg5(world, rank, dev, note):
+    """BASELINE.json config 5: synthetic LP 20M x 40M, 500M nnz (25 per row), row-partitioned over the GPUs of this
+    run with ONE allreduce of the partial K^T y (n + 4 doubles) per iteration -- strong scaling: the LP is the same
+    for every N, every rank generates only its own row block.  Reports ms / iteration of the hot loop, the per-GPU
+    fraction of the HBM roofline, and the time to the reference's termination test at 1e-4."""
+    import torch.distributed as dist
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.sharded import build_rank_engine
+    import scipy.sparse as sp
+    m, n, nnz_row = 20_000_000, 40_000_000, 25
+    t0 = time.perf_counter()
+    rng = np.random.default_rng(0)                       # replicated vectors: the same draw on every rank
+    x_feas = rng.uniform(-10, 10, size=n)
+    l = np.maximum(x_feas - rng.uniform(1, 5, size=n), -1e4)
+    u = np.minimum(x_feas + rng.uniform(1, 5, size=n), 1e4)
+    c = rng.normal(size=n)
+    m_ineq = int(0.8 * m)
+    r0, r1 = rank * m // world, (rank + 1) * m // world
+    Kb = synthetic._stratified_rows(r1 - r0, n, nnz_row, np.random.default_rng(1000 + rank))
+    mi = min(max(m_ineq - r0, 0), r1 - r0)
+    sign = np.ones(r1 - r0)
+    sign[:mi] = -1.0                                     # ">=" rows are -G x >= -h
+    Kb = sp.csr_matrix(sp.diags(sign) @ Kb)
+    Kb.sort_indices()
+    q = Kb @ x_feas
+    q[:mi] -= np.random.default_rng(2000 + rank).uniform(0.1, 5.0, size=mi)
+    t_gen = time.perf_counter() - t0
+    note(f"cfg5 generated in {t_gen:.1f}s")
+    t0 = time.perf_counter()
+    # n = 40M: the LL words of the peer-memory exchange would double the bytes on the wire, NCCL moves plain doubles
+    solver = build_rank_engine(Kb, mi, c, q, l, u, device=dev, exchange="nccl")
+    torch.cuda.synchronize(dev)
+    t_build = time.perf_counter() - t0
+    nnz_local = int(Kb.nnz)
+    del Kb
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    eta, omega, sigma = solver.initial_step(30)
+    torch.cuda.synchronize(dev)
+    t_power = time.perf_counter() - t0
+    p = solver.p
+    p.set_iterate(None, None); p.set_counters(0, 0); p.set_step(eta, omega, 1.0, True); p.set_options(1e-4, True)
+    p.enable(solver.q_norm, solver.c_norm)
+    times = []
+    for b in range(4):                                   # block 0 runs eagerly, block 1 captures the graph
+        dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        solver.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+        solver.restart_check(False)
+    ms_iter = min(times[2:]) / RESTART_PERIOD
+    note(f"cfg5 hot loop {ms_iter:.3f} ms/iteration")
+    # time to tolerance: a fresh solve (same engine, iterate reset) to the reference's termination test
+    dist.barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    torch.manual_seed(0)
+    x, y, obj, k, nres, j, status, secs, sig = solver.solve(adaptive=True, primal_update=True, max_kkt=6_000, power_iters=30)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t_solve = time.perf_counter() - t0
+    a, b = x.clone(), x.clone()
+    dist.all_reduce(a, op=dist.ReduceOp.MIN)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX)
+    same_x = bool(torch.equal(a, b))
+    solver.close()
+    peak, _ = measured_peak()
+    bytes_total = 24 * nnz_row * m + 4 * (m + n + 2) + 72 * n + 48 * m
+    bytes_rank = 24 * nnz_local + 4 * ((r1 - r0) + n + 2) + 72 * n + 48 * (r1 - r0)     # x-side work is replicated
+    return {"workload": f"cfg5: synthetic LP m={m} n={n} nnz={nnz_row * m}, row-partitioned over {world} GPUs (strong scaling), "
+                        "fp64, restarts + adaptive step + primal weight",
+            "exchange": "1 NCCL allreduce of n + 4 doubles per iteration (320 MB)", "n_gpus": world,
+            "ms_per_iteration": ms_iter, "iterations_per_sec": 1e3 / ms_iter,
+            "bytes_per_iteration_total": bytes_total, "aggregate_algorithmic_GBps": bytes_total / (ms_iter * 1e-3) / 1e9,
+            "per_gpu_roofline_frac": bytes_rank / (ms_iter * 1e-3) / 1e9 / peak,
+            "time_to_tolerance": {"rel_kkt": 1e-4, "status": status, "iterations": int(k), "restarts": int(nres),
+                                  "kkt_passes": int(j), "seconds": t_solve, "objective": obj,
+                                  "includes": "30 power-iteration rounds + every restart test"},
+            "x_replicas_bit_identical": same_x, "sigma_max": sigma,
+            "setup_s": {"generate_rank_block": t_gen, "engine_build": t_build, "power_iteration_30": t_power}}
 
 
 def main():

@@ -233,7 +233,8 @@ int pdlp_pock_chambolle(pdlp_handle h);
 int pdlp_get_scaling(pdlp_handle h, void* D_row, void* D_col);
 /* Declare that the problem held by the engine is ALREADY scaled by (D_row, D_col)
  * (data_precond of pdlp_algorithm, :157-163): termination residuals are then taken
- * on the unscaled problem.  Does not touch the data. */
+ * on the unscaled problem.  Does not touch the data.  Both pointers NULL: forget the scaling (termination on the
+ * problem as held: pdlp_algorithm(precondition=False) on an engine that was used with a scaling before). */
 int pdlp_set_scaling(pdlp_handle h, const void* D_row, const void* D_col);
 /* Current (possibly scaled) problem vectors; any pointer may be NULL. */
 int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u);

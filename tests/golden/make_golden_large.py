@@ -27,6 +27,12 @@ CASES = {
     "cfg2_ruiz": (lambda: synthetic.uniform_rows_lp(), [dict(adaptive=True, primal_update=True, ruiz=True)]),
     "cfg3": (lambda: synthetic.infeasible_lp(), [dict(infeasibility_detect=True),
                                                   dict(adaptive=True, primal_update=True, infeasibility_detect=True)]),
+    # config 3 at full size with certificates that FIRE under the reference's semantics (enhancements.py:106-161):
+    # the decoupled contradictory pair (labelled DUAL_INFEASIBLE by the reference's heuristic, which tests the dual
+    # certificate first and accepts a vanishing dx) and a primal ray (labelled PRIMAL_INFEASIBLE the same way)
+    "cfg3_infeasible": (lambda: synthetic.isolated_infeasible_lp(), [dict(infeasibility_detect=True, max_kkt=100_000)]),
+    "cfg3_unbounded": (lambda: synthetic.unbounded_lp(80_000, 20_000, 200_000, 50, seed=0, name="cfg3_unbounded"),
+                       [dict(infeasibility_detect=True, max_kkt=100_000)]),
     "cfg4_small": (lambda: synthetic.powerlaw_rows_lp(160_000, 40_000, 400_000, max_nnz=20_000, name="cfg4_small"),
                    [dict(max_kkt=3000), dict(adaptive=True, primal_update=True, max_kkt=3000)]),
 }

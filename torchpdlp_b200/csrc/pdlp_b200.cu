@@ -717,16 +717,28 @@ static void init_l2_persistence() {
 #endif
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per kernel AND device
+template <typename F>
+static cudaError_t ensure_smem_attr(F* func, int bytes) {
+  static std::mutex mu;
+  static unsigned long long done = 0;       // bit d: set for device d (this instantiation's kernel)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && (done >> dev) & 1ull) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+  return e;
+}
+
 template <class Op>
 static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st,
                                  const void* gathered = nullptr, size_t gathered_bytes = 0) {
   using T = typename Op::value_type;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         StreamCfg<T>::MAX_SMEM_BYTES - 4096);
+  {
+    cudaError_t e = ensure_smem_attr(stream_kernel<Op>, StreamCfg<T>::MAX_SMEM_BYTES - 4096);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(A.grid);
@@ -753,21 +765,6 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
 static inline int ew_blocks(int64_t len, int sms) {
   int64_t b = (len + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sms * 8));
-}
-
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per kernel AND device
-template <typename F>
-static cudaError_t ensure_smem_attr(F* func, int bytes) {
-  static std::mutex mu;
-  static unsigned long long done = 0;       // bit d: set for device d (this instantiation's kernel)
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  std::lock_guard<std::mutex> lock(mu);
-  if (dev < 64 && (done >> dev) & 1ull) return cudaSuccess;
-  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
-  return e;
 }
 
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, size_t smem, cudaStream_t st) {
@@ -1178,8 +1175,7 @@ static cudaError_t enqueue_iterations(EngineT<T>* E, int n_iters, int save_prev,
 
 template <class Op>
 static cudaError_t prep_kernel() {
-  return cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              StreamCfg<typename Op::value_type>::MAX_SMEM_BYTES - 4096);
+  return ensure_smem_attr(stream_kernel<Op>, StreamCfg<typename Op::value_type>::MAX_SMEM_BYTES - 4096);
 }
 
 template <typename T>
@@ -1194,11 +1190,7 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
     const int stages = std::min(E->K.nstages, E->Kt.nstages);
     const int stage_bytes = std::max(E->K.stage_bytes, E->Kt.stage_bytes);
     const int smem = StreamCfg<T>::W * stages * stage_bytes + 128;
-    static bool attr = false;
-    if (!attr) {
-      CU(cudaFuncSetAttribute(block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
-      attr = true;
-    }
+    CU(ensure_smem_attr(block_kernel<T>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
     CU(cudaMemsetAsync(E->blk_bar, 0, sizeof(unsigned int), st));
     SellView<T> vKt = E->Kt.view(), vK = E->K.view();
     BlockArgs<T> a{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->q, E->ysum, E->Y4, E->kty_old, E->S,
@@ -1317,6 +1309,17 @@ static void fill_check(pdlp_check* out, const Scalars& h) {
   out->kkt_previous = h.kkt_prev;
   out->kkt_first_new = h.kkt_first;
   fill_residuals(&out->point, h.point);
+}
+
+// the cached restart-check graphs bake in the scaling state (pointers and the `scaled` flag): drop them when it changes
+template <typename T>
+static void drop_check_graphs(EngineT<T>* E) {
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
+      E->check_graph[a][b] = nullptr;
+      E->check_warm[a][b] = false;
+    }
 }
 
 template <typename T>
@@ -1492,6 +1495,7 @@ static int engine_ruiz(EngineT<T>* E, int max_iter, double eps, int* rounds_out)
   cudaFree(drs);
   cudaFree(dcs);
   B->scaled = true;
+  drop_check_graphs<T>(E);
   if (rounds_out) *rounds_out = rounds;
   rc = repack<T>(E, E->K);
   if (!rc) rc = repack<T>(E, E->Kt);
@@ -1530,6 +1534,7 @@ static int engine_pock_chambolle(EngineT<T>* E) {
   cudaFree(drs);
   cudaFree(dcs);
   B->scaled = true;
+  drop_check_graphs<T>(E);
   rc = repack<T>(E, E->K);
   if (!rc) rc = repack<T>(E, E->Kt);
   if (rc) return rc;
@@ -1813,9 +1818,16 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
   auto elapsed = [&]() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() + o->time_used;
   };
-  cudaEvent_t ev0, ev1;
-  CU(cudaEventCreate(&ev0));
-  CU(cudaEventCreate(&ev1));
+  struct Events {             // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evs;
+  CU(cudaEventCreate(&evs.a));
+  CU(cudaEventCreate(&evs.b));
+  const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
   CU(cudaEventRecord(ev0, st));
   const int period = o->restart_period > 0 ? o->restart_period : 40;
   Scalars h;
@@ -1892,8 +1904,6 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
   CU(cudaEventSynchronize(ev1));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   res->k = k; res->j = j; res->n = n_restart; res->status = status; res->prim_obj = prim_obj;
   res->seconds = elapsed(); res->device_ms = ms; res->n_trace = n_trace; res->reserved = 0;
   return 0;
@@ -2408,6 +2418,14 @@ extern "C" int pdlp_get_scaling(pdlp_handle h, void* D_row, void* D_col) {
 template <typename T>
 static int t_set_scaling(EngineT<T>* E, const void* drow, const void* dcol) {
   pdlp_engine* B = E->base;
+  drop_check_graphs<T>(E);
+  if (!drow && !dcol) {       // back to the unscaled termination test
+    fill_kernel<T><<<ew_blocks(B->m, B->sms), 256, 0, B->stream>>>(E->drow, T(1), (int)B->m);
+    fill_kernel<T><<<ew_blocks(B->n, B->sms), 256, 0, B->stream>>>(E->dcol, T(1), (int)B->n);
+    CU(cudaGetLastError());
+    B->scaled = false;
+    return 0;
+  }
   CU(cudaMemcpyAsync(E->drow, drow, sizeof(T) * (size_t)B->m, cudaMemcpyDeviceToDevice, B->stream));
   CU(cudaMemcpyAsync(E->dcol, dcol, sizeof(T) * (size_t)B->n, cudaMemcpyDeviceToDevice, B->stream));
   B->scaled = true;
@@ -2415,7 +2433,7 @@ static int t_set_scaling(EngineT<T>* E, const void* drow, const void* dcol) {
 }
 extern "C" int pdlp_set_scaling(pdlp_handle h, const void* D_row, const void* D_col) {
   CHECK_HANDLE(h);
-  if (!D_row || !D_col) return fail(PDLP_ERR_INVALID, "null argument");
+  if ((D_row == nullptr) != (D_col == nullptr)) return fail(PDLP_ERR_INVALID, "D_row and D_col must both be given or both be null");
   return DISPATCH(h, t_set_scaling, D_row, D_col);
 }
 

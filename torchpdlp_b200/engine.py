@@ -252,6 +252,11 @@ class Engine:
         check(self.lib.pdlp_get_scaling(self.h, dr.data_ptr(), dc.data_ptr()))
         return dr, dc
 
+    def clear_scaling(self):
+        """Forget a scaling declared with set_scaling: terminate on the problem as held."""
+        check(self.lib.pdlp_set_scaling(self.h, None, None))
+        torch.cuda.synchronize(self.device)
+
     def set_scaling(self, D_row, D_col):
         dr, dc = self._dev(D_row, self.m), self._dev(D_col, self.n)
         check(self.lib.pdlp_set_scaling(self.h, dr.data_ptr(), dc.data_ptr()))

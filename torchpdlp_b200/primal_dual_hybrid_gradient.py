@@ -142,6 +142,8 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
     if precondition and data_precond is not None:
         D_col, D_row = data_precond[0], data_precond[1]
         engine.set_scaling(D_row, D_col)
+    else:
+        engine.clear_scaling()             # a cached engine may carry the scaling of an earlier call
     eta, omega, sigma = initial_step(engine, power_iters, b0)
     lap("initial_step")
     if x_init is not None and y_init is not None:                          # :31-33
