@@ -253,9 +253,16 @@ def run_engine(args):
     e2e_value = world * e2e_iters / e2e_s
     d2h = x_host.numel() * x_host.element_size() + 64
 
+    # ---- config 4 (2M x 4M, ~50M nnz, power-law rows): hot-loop rate on the load-balance stress case ----
+    cfg4 = None
+    if os.environ.get("PDLP_BENCH_CFG4", "1") != "0" and world == 1:
+        eng.close()
+        _cache.clear()
+        torch.cuda.empty_cache()
+        cfg4 = run_cfg4(dev)
     if rank == 0:
         peak, peak_src = measured_peak()
-        b_iter = eng.bytes_per_iteration
+        b_iter = lp.bytes_per_iteration()
         dual_bytes = 12 * lp.nnz + 4 * (lp.m + 1) + 8 * lp.n + 40 * lp.m       # K stream + gather xbar + 5 m-side streams
         primal_bytes = b_iter - dual_bytes                                     # K^T stream + gather y + 8 n-side streams
         # the dominant kernel = the one with the longer launch (K1 on config 2: twice the rows, shorter rows)
@@ -302,10 +309,52 @@ def run_engine(args):
             "cpu_baseline": {"value": cpu_coo, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"8 adaptive PDHG iterations of the oracle port on the same LP, torch sparse COO "
                                        f"(the reference's sparse layout), {cores} threads; torch sparse CSR (MKL): {cpu_csr:.1f} it/s"},
+            "cfg4": cfg4,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cfg4(dev):
+    """BASELINE.json config 4: transportation-style LP 2M x 4M, ~50M nnz, power-law row lengths (2 ... 100 000):
+    microseconds per PDHG iteration of the hot loop (CUDA graph of 80 kernels, adaptive step + primal weight) and the
+    fraction of the HBM roofline.  The gathered pair vector (64 MB) competes with the matrix stream for the 126 MB L2."""
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.engine import Engine
+    from torchpdlp_b200.primal_dual_hybrid_gradient import initial_step
+    t0 = time.perf_counter()
+    lp = synthetic.powerlaw_rows_lp()
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng = Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u, device=dev)
+    torch.cuda.synchronize(dev)
+    t_build = time.perf_counter() - t0
+    torch.manual_seed(0)
+    eta, omega, sigma = initial_step(eng, 20)
+    eng.set_iterate(None, None); eng.set_counters(0, 0); eng.set_step(eta, omega, 1.0, adaptive=True)
+    eng.set_options(1e-4, True, False, 1e-4)
+    for _ in range(3):
+        eng.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
+        eng.restart_check(False)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    blocks = 5
+    e0.record()
+    for _ in range(blocks):
+        eng.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = 1e3 * e0.elapsed_time(e1) / (blocks * RESTART_PERIOD)
+    prim_ms, dual_ms = eng.time_kernels(20)
+    peak, _ = measured_peak()
+    b_iter = lp.bytes_per_iteration()
+    eng.close()
+    return {"workload": f"cfg4: synthetic transportation-style LP m={lp.m} n={lp.n} nnz={lp.nnz}, power-law row lengths, fp64, "
+                        "adaptive step + primal weight", "us_per_iteration": us, "iterations_per_sec": 1e6 / us,
+            "bytes_per_iteration": b_iter, "iteration_roofline_frac": b_iter / (us * 1e-6) / 1e9 / peak,
+            "primal_launch_us": 1e3 * prim_ms, "dual_launch_us": 1e3 * dual_ms, "sigma_max_20_rounds": sigma,
+            "setup_s": {"generate": t_gen, "engine_build": t_build}}
 
 
 def run_sharded(args, world, rank, local, dev):

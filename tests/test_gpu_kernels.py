@@ -282,6 +282,35 @@ def test_layouts_agree(which, cfg1, monkeypatch):
         assert abs(o[2] - outs[0][2]) <= 1e-10 * abs(outs[0][2])
 
 
+@pytest.mark.parametrize("which,window_mb", [("cfg1", "0.008"), ("ragged", "0.03")])
+def test_column_windows_match_the_single_pass(which, window_mb, cfg1, monkeypatch):
+    """K x in column windows (DualWindowOp: what config 5 uses because its pair vector is beyond L2), forced here on
+    small LPs through PDLP_WINDOW_MB: partial row sums carried through 4 / 11 window launches give the single-pass
+    result to rounding, are bitwise reproducible, and drive the same restart decisions."""
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    outs = []
+    for mb in (None, window_mb, window_mb):
+        if mb is None:
+            monkeypatch.delenv("PDLP_WINDOW_MB", raising=False)
+        else:
+            monkeypatch.setenv("PDLP_WINDOW_MB", mb)
+        eng = make_engine(lp)
+        eng.set_iterate(None, None)
+        eng.set_step(0.05, 0.5, 1.0, adaptive=True)
+        eng.set_options(1e-4, True, False, 1e-4)
+        eng.iterate(40, save_previous=True, use_graph=True)
+        chk = eng.restart_check(False)
+        eng.iterate(7, save_previous=False, use_graph=False)
+        x, y = eng.get_iterate()
+        outs.append((x.cpu(), y.cpu(), eng.state().eta, chk.kind, chk.use_average, chk.kkt_current))
+        eng.close()
+    a, b, c = outs
+    assert torch.equal(b[0], c[0]) and torch.equal(b[1], c[1]) and b[2:] == c[2:]          # reproducible
+    sx, sy = float(a[0].abs().max()) + 1.0, float(a[1].abs().max()) + 1.0
+    assert float((a[0] - b[0]).abs().max()) <= 1e-10 * sx and float((a[1] - b[1]).abs().max()) <= 1e-10 * sy
+    assert abs(a[2] - b[2]) <= 1e-10 * abs(a[2]) and a[3:5] == b[3:5] and abs(a[5] - b[5]) <= 1e-9 * abs(a[5])
+
+
 def test_bitwise_reproducible(cfg1):
     """No atomics on data: two runs of 80 iterations give bit-identical iterates."""
     outs = []

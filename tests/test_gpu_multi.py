@@ -59,7 +59,19 @@ def run_world(exchange, adaptive, pw, which="cfg1", world=2):
     procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, adaptive, pw, which, out)) for r in range(world)]
     for p in procs:
         p.start()
-    res = out.get(timeout=600)
+    import queue
+    import time
+    res, t0 = None, time.time()
+    while res is None:                         # fail fast when a rank dies instead of waiting for the queue's timeout
+        try:
+            res = out.get(timeout=5)
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 600:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"a rank exited with {dead}" if dead else "timed out waiting for rank 0")
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

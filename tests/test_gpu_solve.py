@@ -169,8 +169,10 @@ def test_cfg2_full_size_against_oracle(idx):
 
 @pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
 def test_sharded_peer_exchange_single_rank(adaptive, pw, cfg1):
-    """The peer-memory exchange kernels (flags, segment reduce/push, deferred rule) with world size 1: the same
-    k / n / j / objective as the host-allreduce path, which the next test pins to the executed reference."""
+    """The peer-memory exchange (LL words pushed from the SpMV epilogue, segment reduce / broadcast, deferred rule, all
+    in shard_fused_kernel) with world size 1 against the host-allreduce path, which the next test pins to the executed
+    reference.  Fixed step: identical k / n / j and objective.  Adaptive: the two paths reduce ||dx||^2 over different
+    launch geometries, i.e. in a different (fixed) order, so they agree within the adaptive band."""
     from torchpdlp_b200.sharded import build_rank_engine
     torch.set_default_dtype(torch.float64)
     outs = []
@@ -180,6 +182,10 @@ def test_sharded_peer_exchange_single_rank(adaptive, pw, cfg1):
         x, y, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=pw)
         outs.append((x.cpu(), y.cpu(), obj, k, n, j, status))
         solver.close()
+    if adaptive:
+        assert outs[0][4] == outs[1][4] and outs[0][6] == outs[1][6]            # restarts, status
+        assert abs(outs[0][3] - outs[1][3]) <= 40 and rel(outs[0][2], outs[1][2]) < ADAPTIVE_REL
+        return
     assert outs[0][2:] == outs[1][2:]
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <functional>
 #include <mutex>
 #include <chrono>
@@ -646,6 +647,7 @@ struct EngineT {
   pdlp_engine* base;
   DeviceCsr<T> K, Kt;
   T *c = nullptr, *q = nullptr, *l = nullptr, *u = nullptr;
+  Quad<T>* clu = nullptr;                 // (c, l, u, 0) records for the primal epilogue
   Pair<T>* xp = nullptr;
   T *y = nullptr, *xsum = nullptr, *ysum = nullptr, *xlast = nullptr, *ylast = nullptr;
   Quad<T>*X4 = nullptr, *Y4 = nullptr;
@@ -679,6 +681,19 @@ struct EngineT {
     unsigned int* cticket = nullptr;
     PanelInfo info() const { return PanelInfo{cta_panel, panel_begin, panel_cap}; }
   } panel;
+  // K in column windows for operands larger than L2 (DualWindowOp, pdlp_ops.cuh): the window matrix (P * m rows,
+  // window-relative columns) in CSR, one SELL copy per window (each planned for the whole grid: the windows are
+  // separate launches), the partial (K xbar, K dx) pairs carried between them
+  struct Windows {
+    bool on = false;
+    int P = 0;
+    std::vector<int> begin;              // P + 1 column offsets
+    int* d_begin = nullptr;
+    int *rowptr = nullptr, *colidx = nullptr;
+    T* vals = nullptr;
+    std::vector<DeviceCsr<T>> M;
+    Pair<T>* part = nullptr;
+  } win;
 };
 
 // stream-ordered allocation from the device's default pool (kept cached: building an engine right after another
@@ -717,19 +732,24 @@ static void init_l2_persistence() {
 #endif
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per kernel AND device
-template <typename F>
-static cudaError_t ensure_smem_attr(F* func, int bytes) {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per kernel (its address -- two
+// instantiations may share a function type) AND device
+static cudaError_t ensure_smem_attr_impl(const void* func, int bytes) {
   static std::mutex mu;
-  static unsigned long long done = 0;       // bit d: set for device d (this instantiation's kernel)
+  static std::vector<std::pair<const void*, int>> done;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(mu);
-  if (dev < 64 && (done >> dev) & 1ull) return cudaSuccess;
+  for (const auto& d : done)
+    if (d.first == func && d.second == dev) return cudaSuccess;
   e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+  if (e == cudaSuccess) done.emplace_back(func, dev);
   return e;
+}
+template <typename F>
+static cudaError_t ensure_smem_attr(F* func, int bytes) {
+  return ensure_smem_attr_impl(reinterpret_cast<const void*>(func), bytes);
 }
 
 template <class Op>
@@ -813,6 +833,18 @@ static cudaError_t launch_panel_combine(EngineT<T>* E, Op op, const T* in, cudaS
   return cudaLaunchKernelEx(&cfg, combine_kernel<Op>, (const T*)P.partial, P.P, rows, op, P.cpartials, P.cticket);
 }
 
+// PDLP_TRACE_SETUP=1: wall-clock of the setup stages on stderr (developer aid)
+struct SetupTrace {
+  bool on = getenv("PDLP_TRACE_SETUP") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pdlp setup] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 // fill the run-layout chunks / the panel matrix from the CSR master copy
 template <typename T>
 static int pack_run(EngineT<T>* E, DeviceCsr<T>& A) {
@@ -841,6 +873,9 @@ static int pack_panels(EngineT<T>* E, bool with_columns) {
   return 0;
 }
 
+template <typename T>
+static int pack_windows(EngineT<T>* E, bool with_columns);
+
 // (re)fill the packed copy from the CSR master copy (after create and after every scaling pass)
 template <typename T>
 static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
@@ -852,7 +887,7 @@ static int repack(EngineT<T>* E, DeviceCsr<T>& A) {
   int rc = pack_run<T>(E, A);
   if (rc) return rc;
   if (&A == &E->Kt) return pack_panels<T>(E, false);
-  return 0;
+  return pack_windows<T>(E, false);
 }
 
 // PDLP_LAYOUT selects the layout of the two iteration kernels when the engine is created:
@@ -963,17 +998,108 @@ static int build_panels(EngineT<T>* E) {
   return 0;
 }
 
-// PDLP_TRACE_SETUP=1: wall-clock of the setup stages on stderr (developer aid)
-struct SetupTrace {
-  bool on = getenv("PDLP_TRACE_SETUP") != nullptr;
-  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-  void lap(const char* what) {
-    if (!on) return;
-    const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[pdlp setup] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
-    t = now;
+// K in column windows: only when the gathered pair vector is well beyond L2 (config 5); PDLP_WINDOW_MB overrides the
+// window size (MB of pairs per window, 0 = never)
+template <typename T>
+static int pack_windows(EngineT<T>* E, bool with_columns) {
+  pdlp_engine* B = E->base;
+  auto& W = E->win;
+  const DeviceCsr<T>& A = E->K;
+  if (!W.on) return 0;
+  panel_fill_kernel<T><<<ew_blocks(A.rows, B->sms), 256, 0, B->stream>>>(A.rowptr, A.colidx, A.vals, A.rows, W.d_begin, W.P,
+                                                                        W.rowptr, with_columns ? W.colidx : nullptr, W.vals);
+  CU(cudaGetLastError());
+  for (auto& M : W.M)
+    if (M.npieces > 0) {
+      pack_kernel<T><<<std::min(M.npieces, B->sms * 16), 256, 0, B->stream>>>(M.pieces, M.perm, M.npieces, M.rowptr, M.colidx,
+                                                                             M.vals, M.packed);
+      CU(cudaGetLastError());
+    }
+  return 0;
+}
+
+template <typename T>
+static int build_windows(EngineT<T>* E) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  DeviceCsr<T>& A = E->K;
+  using Cfg = StreamCfg<T>;
+  auto& W = E->win;
+  const char* env = getenv("PDLP_WINDOW_MB");
+  const double window_mb = env ? atof(env) : 64.0;
+  const double table_mb = (double)A.cols * sizeof(Pair<T>) / 1e6;
+  if (window_mb <= 0.0 || table_mb <= 1.5 * window_mb) return 0;
+  const int P = (int)std::ceil(table_mb / window_mb);
+  if (P < 2 || P > PANEL_MAX) return 0;
+  const int width = ((A.cols + P - 1) / P + 3) / 4 * 4;
+  W.begin.assign((size_t)P + 1, A.cols);
+  for (int p = 0; p < P; ++p) W.begin[p] = std::min(A.cols, p * width);
+  W.P = P;
+  SetupTrace tr;
+  ALLOC(W.d_begin, W.begin.size());
+  CU(cudaMemcpyAsync(W.d_begin, W.begin.data(), sizeof(int) * W.begin.size(), cudaMemcpyHostToDevice, st));
+  int* d_cnt = nullptr;
+  ALLOC(d_cnt, (size_t)P * A.rows);
+  panel_count_kernel<<<ew_blocks(A.rows, B->sms), 256, 0, st>>>(A.rowptr, A.colidx, A.rows, W.d_begin, P, d_cnt);
+  CU(cudaGetLastError());
+  std::vector<int> cnt((size_t)P * A.rows);
+  CU(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::vector<int> rowptr((size_t)P * A.rows + 1);
+  long long pos = 0;
+  for (size_t i = 0; i < cnt.size(); ++i) {
+    rowptr[i] = (int)pos;
+    pos += cnt[i];
   }
-};
+  rowptr[cnt.size()] = (int)pos;
+  if (pos != A.nnz) return fail(PDLP_ERR_STATE, "column windows do not cover the matrix");
+  ALLOC(W.rowptr, rowptr.size());
+  ALLOC(W.colidx, (size_t)A.nnz + 1);
+  ALLOC(W.vals, (size_t)A.nnz + 1);
+  ALLOC(W.part, A.rows);
+  CU(cudaMemcpyAsync(W.rowptr, rowptr.data(), sizeof(int) * rowptr.size(), cudaMemcpyHostToDevice, st));
+  tr.lap("windows: counts + row pointers");
+  W.M.resize(P);
+  for (int p = 0; p < P; ++p) {
+    // every window is an ordinary SELL matrix of A.rows rows on a slice of the window matrix's CSR arrays; a row part
+    // reads and writes the carried pair (2 sector operations) instead of the full dual epilogue
+    HostSell S = build_sell_plan(rowptr.data() + (size_t)p * A.rows, A.rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA,
+                                 PDLP_LONG_ROW, PDLP_WARP_ROW, B->sms * PDLP_CTAS * PDLP_OVERSUB, 2.0);
+    DeviceCsr<T>& M = W.M[p];
+    M.rows = A.rows; M.cols = W.begin[p + 1] - W.begin[p]; M.nnz = rowptr[(size_t)(p + 1) * A.rows] - rowptr[(size_t)p * A.rows];
+    M.rowptr = W.rowptr + (size_t)p * A.rows;          // entries are offsets into the shared colidx / vals arrays
+    M.colidx = W.colidx;
+    M.vals = W.vals;
+    M.stage_bytes = (S.max_piece_bytes + 127) / 128 * 128;
+    M.nstages = std::max(2, std::min(Cfg::SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)Cfg::W * M.stage_bytes))));
+    M.smem_bytes = Cfg::W * M.nstages * M.stage_bytes + 128;
+    if (S.packed_bytes / 16 >= 0xffffffffull) return fail(PDLP_ERR_INVALID, "packed window exceeds 64 GiB");
+    M.grid = S.grid; M.npieces = (int)S.pieces.size(); M.nlong = (int)S.long_rows.size(); M.packed_bytes = S.packed_bytes;
+    ALLOC(M.packed, S.packed_bytes + 16);
+    ALLOC(M.pieces, S.pieces.size() + 1);
+    ALLOC(M.perm, S.perm.size() + 32);
+    ALLOC(M.warp_begin, S.warp_begin.size());
+    ALLOC(M.long_rows, S.long_rows.size() + 1);
+    ALLOC(M.partials, (size_t)S.grid * MAX_RED);
+    ALLOC(M.ticket, 1);
+    CU(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned int), st));
+    CU(cudaMemcpyAsync(M.pieces, S.pieces.data(), sizeof(Piece) * S.pieces.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(M.perm, S.perm.data(), sizeof(int) * S.perm.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(M.warp_begin, S.warp_begin.data(), sizeof(int) * S.warp_begin.size(), cudaMemcpyHostToDevice, st));
+    if (!S.long_rows.empty())
+      CU(cudaMemcpyAsync(M.long_rows, S.long_rows.data(), sizeof(int) * S.long_rows.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));    // S goes out of scope
+  }
+  W.on = true;
+  int rc = pack_windows<T>(E, true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));
+  tr.lap("windows: plans + pack");
+  if (getenv("PDLP_TRACE_SETUP"))
+    fprintf(stderr, "[pdlp setup] K in %d column windows of %d columns (%.0f MB of pairs each)\n", P, width,
+            (double)width * sizeof(Pair<T>) / 1e6);
+  return 0;
+}
 
 template <typename T>
 static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nnz, const int32_t* rowptr,
@@ -1057,13 +1183,15 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
     if (!E->Kt.run_on) E->k1 = 0;
   }
   if (E->k1 == 1 || E->k2 == 1) tr.lap("run layout");
+  rc = build_windows<T>(E);
+  if (rc) return rc;
   if (E->k1 == 2) {
     rc = build_panels<T>(E);
     if (rc) return rc;
     if (!E->panel.on) E->k1 = 0;
     tr.lap("K^T panels");
   }
-  ALLOC(E->c, n); ALLOC(E->l, n); ALLOC(E->u, n); ALLOC(E->q, m);
+  ALLOC(E->c, n); ALLOC(E->l, n); ALLOC(E->u, n); ALLOC(E->q, m); ALLOC(E->clu, n);
   ALLOC(E->xp, n); ALLOC(E->xsum, n); ALLOC(E->xlast, n); ALLOC(E->X4, n);
   ALLOC(E->y, m + 4);      // the panel kernel's bulk copies round the last panel up to 16 bytes
   ALLOC(E->ysum, m); ALLOC(E->ylast, m); ALLOC(E->Y4, m);
@@ -1087,6 +1215,7 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   CU(cudaMemcpyAsync(E->l, l, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(E->u, u, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(E->q, q, sizeof(T) * m, cudaMemcpyDeviceToDevice, st));
+  pack_clu_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->c, E->l, E->u, E->clu, n);
   CU(cudaMemsetAsync(E->X4, 0, sizeof(Quad<T>) * n, st));
   CU(cudaMemsetAsync(E->Y4, 0, sizeof(Quad<T>) * m, st));
   fill_kernel<T><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->drow, T(1), m);
@@ -1141,17 +1270,36 @@ static int refresh_norms(EngineT<T>* E) {
 // ---------------------------------------------------------------------------
 // hot loop
 // ---------------------------------------------------------------------------
+// K2 (K xbar + dual update + step rule) in whichever form the engine holds K: column windows (operand beyond L2; not
+// with infeasibility detection), the run layout, or SELL
+template <typename T, bool SP, bool INF>
+static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st) {
+  if (!INF && E->win.on) {
+    auto& W = E->win;
+    cudaError_t e = cudaSuccess;
+    for (int p = 0; p < W.P && e == cudaSuccess; ++p) {
+      DualOp<T, SP, false> d{E->xp + W.begin[p], E->q, E->y, E->ysum, E->Y4, E->S};
+      if (p == 0) e = launch_stream(W.M[p], DualWindowOp<T, true, false, SP>{d, W.part}, st);
+      else if (p + 1 < W.P) e = launch_stream(W.M[p], DualWindowOp<T, false, false, SP>{d, W.part}, st);
+      else e = launch_stream(W.M[p], DualWindowOp<T, false, true, SP>{d, W.part}, st);
+    }
+    return e;
+  }
+  DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+  if (E->k2 == 1) return launch_run(E->K, d, st);
+  return launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
+}
+
 template <typename T, bool SP, bool INF>
 static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
   PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
+  p.clu = E->clu;
   cudaError_t e;
   if (E->k1 == 2) e = launch_panel_combine<T>(E, p, (const T*)E->y, st);
   else if (E->k1 == 1) e = launch_run(E->Kt, p, st);
   else e = launch_stream(E->Kt, p, st, E->y, sizeof(T) * (size_t)E->base->m);
   if (e != cudaSuccess) return e;
-  DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-  if (E->k2 == 1) e = launch_run(E->K, d, st);
-  else e = launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
+  e = launch_dual<T, SP, INF>(E, st);
   if (e != cudaSuccess) return e;
   if (INF) {
     InfeasColsOp<T> f{E->y, E->c, E->l, E->u, E->kty_old, E->lam_prev, E->S};
@@ -1223,6 +1371,14 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   CU((prep_kernel<DualOp<T, true, true>>()));
   CU((prep_kernel<DualOp<T, false, true>>()));
   CU((prep_kernel<InfeasColsOp<T>>()));
+  if (E->win.on) {
+    CU((prep_kernel<DualWindowOp<T, true, false, true>>()));
+    CU((prep_kernel<DualWindowOp<T, true, false, false>>()));
+    CU((prep_kernel<DualWindowOp<T, false, false, true>>()));
+    CU((prep_kernel<DualWindowOp<T, false, false, false>>()));
+    CU((prep_kernel<DualWindowOp<T, false, true, true>>()));
+    CU((prep_kernel<DualWindowOp<T, false, true, false>>()));
+  }
   if (E->k1 || E->k2) {
     CU((prep_run_kernel<PrimalOp<T, true, false>>()));
     CU((prep_run_kernel<PrimalOp<T, false, false>>()));
@@ -1258,14 +1414,13 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
   for (auto& e : ev) CU(cudaEventCreate(&e));
   for (int i = 0; i < n_iters; ++i) {
     PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
-    DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    p.clu = E->clu;
     CU(cudaEventRecord(ev[3 * i], st));
     if (E->k1 == 2) CU(launch_panel_combine<T>(E, p, (const T*)E->y, st));
     else if (E->k1 == 1) CU(launch_run(E->Kt, p, st));
     else CU(launch_stream(E->Kt, p, st));
     CU(cudaEventRecord(ev[3 * i + 1], st));
-    if (E->k2 == 1) CU(launch_run(E->K, d, st));
-    else CU(launch_stream(E->K, d, st));
+    CU((launch_dual<T, false, false>(E, st)));
     CU(cudaEventRecord(ev[3 * i + 2], st));
   }
   CU(cudaStreamSynchronize(st));
@@ -1452,6 +1607,7 @@ static int apply_vector_scaling(EngineT<T>* E, const T* drow_step, const T* dcol
   vec_scale_kernel<T, 0><<<ew_blocks(m, B->sms), 256, 0, st>>>(E->q, drow_step, m);
   vec_scale_kernel<T, 1><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->l, dcol_step, n);
   vec_scale_kernel<T, 1><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->u, dcol_step, n);
+  pack_clu_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->c, E->l, E->u, E->clu, n);
   CU(cudaGetLastError());
   return 0;
 }
@@ -1592,14 +1748,12 @@ static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
   if (save_prev) {
     shard_primal_kernel<T, true><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
                                                              E->ew_partials, E->ew_ticket);
-    DualOp<T, true, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-    CU(launch_stream(E->K, d, st));
+    CU((launch_dual<T, true, false>(E, st)));
     B->have_prev = true;
   } else {
     shard_primal_kernel<T, false><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
                                                               E->ew_partials, E->ew_ticket);
-    DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-    CU(launch_stream(E->K, d, st));
+    CU((launch_dual<T, false, false>(E, st)));
   }
   CU(cudaGetLastError());
   return 0;
@@ -1710,33 +1864,25 @@ static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
   cudaStream_t st = B->stream;
   if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
   if (!B->xchg_connected) return fail(PDLP_ERR_INVALID, "pdlp_shard_exchange_connect has not been called");
-  double* part = (double*)B->xchg_block;
-  const int xg = std::min(E->ew_grid, B->sms * 2);      // co-resident: at most 2 CTAs of 256 threads per SM
+  if (E->Kt.grid > B->sms) return fail(PDLP_ERR_STATE, "the fused exchange needs a co-resident grid");
+  CU(ensure_smem_attr(shard_fused_kernel<T, true>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
+  CU(ensure_smem_attr(shard_fused_kernel<T, false>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
   for (int i = 0; i < n_iters; ++i) {
     const bool save = save_prev && i == n_iters - 1;
-    ShardKtyOp<T> f{E->y, part, E->S};
-    CU(launch_stream(E->Kt, f, st));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(xg);
-    cfg.blockDim = dim3(256);
-    cfg.stream = st;
+    // column side: SpMV + exchange + step rule + primal update in ONE kernel; row side: the ordinary DualOp
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    pdl_config(cfg, attr, E->Kt.grid, StreamCfg<T>::NT, (size_t)E->Kt.smem_bytes, st);
     const Xchg* xd = B->xchg_dev;
     if (save) {
-      CU(cudaLaunchKernelEx(&cfg, xchg_primal_kernel<T, true>, xd, (const T*)E->c, (const T*)E->l, (const T*)E->u, E->xp,
-                            E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
-      DualOp<T, true, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-      CU(launch_stream(E->K, d, st));
+      CU(cudaLaunchKernelEx(&cfg, shard_fused_kernel<T, true>, E->Kt.view(), xd, (const T*)E->y, (const T*)E->c,
+                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
+      CU((launch_dual<T, true, false>(E, st)));
       B->have_prev = true;
     } else {
-      CU(cudaLaunchKernelEx(&cfg, xchg_primal_kernel<T, false>, xd, (const T*)E->c, (const T*)E->l, (const T*)E->u, E->xp,
-                            E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
-      DualOp<T, false, false> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
-      CU(launch_stream(E->K, d, st));
+      CU(cudaLaunchKernelEx(&cfg, shard_fused_kernel<T, false>, E->Kt.view(), xd, (const T*)E->y, (const T*)E->c,
+                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
+      CU((launch_dual<T, false, false>(E, st)));
     }
     CU(cudaGetLastError());
   }

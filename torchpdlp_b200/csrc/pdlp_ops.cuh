@@ -191,6 +191,8 @@ struct PrimalOp {
   T* kty_old;        // INFEAS: K^T y of the iterate the step started from
   T tau, wpend, itol;
   bool do_save = true;   // runtime gate of SAVE_PREV (the persistent kernel saves only on its last iteration)
+  const Quad<T>* clu = nullptr;   // (c, l, u, 0) records: one 32-byte sector per row instead of three (sigma-sorted rows
+                                  // make every epilogue access its own sector, section 4b of DESIGN.md)
   __device__ bool begin() {
     if (S->stop) return false;
     tau = (T)(S->eta / S->omega);
@@ -200,7 +202,13 @@ struct PrimalOp {
   }
   __device__ T gather(int col) const { return ldg_keep(y + col); }
   __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
-  __device__ Ctx row_load(int j) const { return Ctx{c[j], l[j], u[j], xp[j].a, xsum[j]}; }
+  __device__ Ctx row_load(int j) const {
+    if (clu) {
+      const Quad<T> r = clu[j];
+      return Ctx{r.v[0], r.v[1], r.v[2], xp[j].a, xsum[j]};
+    }
+    return Ctx{c[j], l[j], u[j], xp[j].a, xsum[j]};
+  }
   __device__ void row_finish(int j, const Ctx& k, const T (&acc)[1], double (&red)[NRED]) {
     const T g = k.c - acc[0];
     const T xn = clampv(k.xo - tau * g, k.l, k.u);
@@ -307,6 +315,44 @@ struct DualOp {
       }
     }
     commit_step(s, w, next);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K2 in column windows (operands larger than L2, config 5): K is cut into P column windows whose slice of the
+// (x, dx) pair vector stays L2-resident; window p is one launch over the sub-matrix K[:, window p] (columns relative
+// to the window) that adds its two partial row sums (K xbar, K dx) to the pair carried in part[] -- read unless
+// FIRST, written unless LAST; the LAST window runs DualOp's epilogue on the totals.  Fixed window order: reproducible.
+// ---------------------------------------------------------------------------
+template <typename T, bool FIRST, bool LAST, bool SAVE_PREV>
+struct DualWindowOp {
+  using value_type = T;
+  using Gather = Pair<T>;
+  using Inner = DualOp<T, SAVE_PREV, false>;
+  struct Ctx { Pair<T> part; typename Inner::Ctx in; };
+  static constexpr int NV = 2;
+  static constexpr int NRED = LAST ? Inner::NRED : 0;
+  static constexpr int UDIV = 1;
+  static constexpr int PIPE = 0;
+  Inner d;               // d.xp already points at the window's first pair
+  Pair<T>* part;
+  __device__ bool begin() { return d.begin(); }
+  __device__ Pair<T> gather(int col) const { return d.gather(col); }
+  __device__ void mac(T (&acc)[2], T a, const Pair<T>& p) const { d.mac(acc, a, p); }
+  __device__ Ctx row_load(int i) const {
+    Ctx c;
+    if (!FIRST) c.part = ldg(part + i);
+    if (LAST) c.in = d.row_load(i);
+    return c;
+  }
+  __device__ void row_finish(int i, const Ctx& k, const T (&acc)[2], double (&red)[NRED > 0 ? NRED : 1]) {
+    T a[2] = {acc[0], acc[1]};
+    if (!FIRST) { a[0] = k.part.a + a[0]; a[1] = k.part.b + a[1]; }
+    if constexpr (LAST) d.row_finish(i, k.in, a, red);
+    else part[i] = Pair<T>{a[0], a[1]};
+  }
+  __device__ void finalize(const double (&tot)[NRED > 0 ? NRED : 1]) {
+    if constexpr (LAST) d.finalize(tot);
   }
 };
 
@@ -642,11 +688,12 @@ __global__ void shard_rule_kernel(Scalars* S, const double* tail) {
 // no flags, fences or acquire/release round trips, and nothing to reset (seq only grows).  (The accessors are
 // volatile asm without a memory clobber: ordered among themselves, but ordinary loads may be scheduled around them.)  One exchange is a
 // two-shot allreduce:
-//   ShardKtyOp (the K_g^T y_g SpMV)  writes part[] locally, its last CTA appends the pending step-rule partials
-//   xchg_kernel   phase 1: every rank stores segment s of its part[] into recv[rank] of rank s (NVLink stores)
-//                 phase 2: rank s polls its recv[*] slots, sums them in rank order and stores the sums into
-//                          tot[] of every rank (NVLink stores)
-//   xchg_rule_kernel / shard_primal_kernel poll tot[] locally.
+//   shard_fused_kernel   its SpMV epilogue (ShardPushOp) stores the partial sum of column j straight into recv[rank]
+//                        of the rank that owns j -- NVLink stores issued while the SpMV is still running;
+//                 then   every rank polls its recv[*] slots, sums them in rank order and stores the sums into tot[]
+//                        of every rank (NVLink stores), evaluates the step rule from the tail and updates x as its
+//                        share of tot[] arrives (xchg_reduce_rule_primal).
+//   xchg_allreduce_kernel  the same two phases for a caller's buffer (restart test, power iteration).
 // Each segment is summed by exactly one rank, so all ranks see bit-identical totals.  The grid of xchg_kernel is
 // co-resident (phase 2 of one GPU waits for phase 1 of the others, never for its own later CTAs).  A poll that
 // lasts longer than XCHG_TIMEOUT_NS sets Scalars::xchg_error + stop instead of hanging the GPU.
@@ -715,38 +762,10 @@ __device__ __forceinline__ double ll_wait(const uint4* p, unsigned int seq, Scal
   return ll_wait(p, seq, S, ll_load(p));
 }
 
-// rows of K_g^T: part[j] = (K_g^T y_g)[j]; the last CTA appends the pending step-rule partials
-template <typename T>
-struct ShardKtyOp {
-  using value_type = T;
-  using Gather = T;
-  using Ctx = NoCtx;
-  static constexpr int NV = 1;
-  static constexpr int NRED = 1;      // nothing to reduce: NRED > 0 buys the "last CTA" finalize
-  static constexpr int UDIV = 1;
-  static constexpr int PIPE = 1;
-  const T* in;
-  double* part;                       // this rank's part[]: tail, then the columns
-  Scalars* S;
-  __device__ bool begin() { return true; }      // never skipped: the peers wait for this rank's data
-  __device__ T gather(int col) const { return ldg(in + col); }
-  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
-  __device__ Ctx row_load(int) const { return Ctx{}; }
-  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) { part[XCHG_TAIL + r] = (double)acc[0]; }
-  __device__ void finalize(const double (&)[1]) {
-    const Scalars& s = *S;
-    part[0] = s.rule_pending ? s.dy2 : 0.0;
-    part[1] = s.rule_pending ? s.inter : 0.0;
-    part[2] = 0.0;
-    part[3] = 0.0;
-  }
-};
-
-// phases 1 and 2 of an exchange of src[0 .. count): scatter to the owners, reduce the owned segment, broadcast.
-// All loads of a batch are issued before the first one is inspected (volatile loads are not reordered by the
-// compiler, so a loop of ll_wait would pay one L2 / NVLink latency per peer).
-__device__ __forceinline__ void xchg_scatter_reduce(const Xchg& X, const double* src, int count, unsigned int seq,
-                                                    Scalars* S, int tid, int nthr) {
+// Phase 1 of an exchange of src[0 .. count): every element goes to the recv[] slot of its owner.
+// All loads of a batch are issued before the first store (volatile accesses are not reordered by the compiler).
+__device__ __forceinline__ void xchg_scatter(const Xchg& X, const double* src, int count, unsigned int seq, int tid,
+                                             int nthr) {
   constexpr int NB = 4;
   for (int e0 = tid; e0 < count; e0 += NB * nthr) {
     double v[NB];
@@ -762,6 +781,11 @@ __device__ __forceinline__ void xchg_scatter_reduce(const Xchg& X, const double*
       }
     }
   }
+}
+// Phase 2: this rank sums, in rank order, the slots of the segment it owns as they arrive and stores the totals into
+// tot[] of every rank.  All loads of a batch are issued before the first one is inspected (a loop of ll_wait would
+// pay one L2 / NVLink latency per peer).
+__device__ __forceinline__ void xchg_reduce_owned(const Xchg& X, int count, unsigned int seq, Scalars* S, int tid, int nthr) {
   const int s0 = X.rank * X.seg;
   const int len = max(0, min(count, s0 + X.seg) - s0);
   const uint4* mine = X.recv[X.rank];
@@ -778,6 +802,11 @@ __device__ __forceinline__ void xchg_scatter_reduce(const Xchg& X, const double*
     }
     for (int p = 0; p < X.world; ++p) ll_store(X.tot[p] + s0 + i, a, seq);
   }
+}
+__device__ __forceinline__ void xchg_scatter_reduce(const Xchg& X, const double* src, int count, unsigned int seq,
+                                                    Scalars* S, int tid, int nthr) {
+  xchg_scatter(X, src, count, seq, tid, nthr);
+  xchg_reduce_owned(X, count, seq, S, tid, nthr);
 }
 
 // stand-alone allreduce (sum) of buf[0 .. count) over the same exchange block, count <= L: the small collectives of
@@ -849,28 +878,18 @@ __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, c
   }
 }
 
-// The exchange and the primal update in ONE kernel (pdlp_shard_iterate_p2p): phases 1-2 of xchg_kernel, then every
-// CTA polls the tail of tot[], evaluates the pending step rule for itself (read-only on Scalars), polls its share
-// of tot[] and updates x; the last CTA -- every reader of Scalars is done by then -- commits the rule, ||dx||^2 and
-// the sequence number.  The grid must be co-resident (<= 2 CTAs of 256 threads per SM).
+// Everything of a sharded iteration's column side that follows the scatter of the partial K_g^T y_g: reduce the owned
+// segment and broadcast it, then every CTA polls the tail of tot[], evaluates the pending step rule for itself
+// (read-only on Scalars), polls its share of tot[] and updates x; the last CTA -- every reader of Scalars is done by
+// then -- commits the rule, ||dx||^2 and the sequence number.  The grid must be co-resident.  sh: >= blockDim / 32
+// doubles, s_rule: 6 doubles, s_int: 3 ints of shared memory.
 template <typename T, bool SAVE_PREV>
-__global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const T* c, const T* l, const T* u,
-                                                          Pair<T>* xp, T* xsum, Quad<T>* X4, Scalars* S,
-                                                          double* partials, unsigned int* ticket) {
-  __shared__ Xchg X;
-  __shared__ double sh[32];
-  __shared__ double s_rule[4];      // eta (post rule), w_pending (post rule), dy2, inter
-  __shared__ double s_w, s_next;
-  __shared__ int s_last, s_stop, s_pending;
-  xchg_load(X, Xp);
-  // programmatic dependent launch: resident while the SpMV before it drains, the dual kernel after it may prefetch
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  __syncthreads();
-  const unsigned int seq = (unsigned int)S->xchg_seq;
+__device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned int seq, const T* c, const T* l, const T* u,
+                                                        Pair<T>* xp, T* xsum, Quad<T>* X4, Scalars* S, double* partials,
+                                                        unsigned int* ticket, double* sh, double* s_rule, int* s_int) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthr = gridDim.x * blockDim.x;
-  xchg_scatter_reduce(X, X.part, X.L, seq, S, tid, nthr);
+  xchg_reduce_owned(X, X.L, seq, S, tid, nthr);
   const uint4* tot = X.tot[X.rank];
   if (threadIdx.x == 0) {
     const uint4 v0 = ll_load(tot + 0), v1 = ll_load(tot + 1);
@@ -883,12 +902,12 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
       eta = next;
       wp = w;
     }
-    s_rule[0] = eta; s_rule[1] = wp; s_rule[2] = dy2; s_rule[3] = inter;
-    s_w = w; s_next = next;
-    s_pending = pending;
-    s_stop = S->stop;
+    s_rule[0] = eta; s_rule[1] = wp; s_rule[2] = dy2; s_rule[3] = inter; s_rule[4] = w; s_rule[5] = next;
+    s_int[1] = pending;
+    s_int[2] = S->stop;
   }
   __syncthreads();
+  const int s_stop = s_int[2];
   double dx2 = 0.0;
   if (!s_stop) {
     const T tau = (T)(s_rule[0] / S->omega);
@@ -926,6 +945,7 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+  __syncthreads();          // sh may still be in use by the caller's earlier phase
   if (lane == 0) sh[warp] = dx2;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -933,17 +953,17 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
     partials[blockIdx.x] = a;
     __threadfence();
-    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    s_int[0] = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_int[0] && threadIdx.x == 0) {
     __threadfence();
     Scalars& s = *S;
-    if (s_pending) {          // commit the rule every CTA evaluated (shard_rule_kernel's arithmetic)
+    if (s_int[1]) {           // commit the rule every CTA evaluated (shard_rule_kernel's arithmetic)
       s.k += 1;
       s.dy2 = s_rule[2];
       s.inter = s_rule[3];
-      commit_step(s, s_w, s_next);
+      commit_step(s, s_rule[4], s_rule[5]);
       s.rule_pending = 0;
     }
     if (!s_stop) {
@@ -954,6 +974,81 @@ __global__ void __launch_bounds__(256) xchg_primal_kernel(const Xchg* Xp, const 
     s.xchg_seq = (unsigned long long)seq + 1;
     *ticket = 0u;
   }
+}
+
+// rows of K_g^T: the partial sum of column j goes, as an LL word, straight into the recv[] slot of the rank that owns
+// it -- over NVLink while the SpMV is still running, no staging copy in HBM
+template <typename T>
+struct ShardPushOp {
+  using value_type = T;
+  using Gather = T;
+  using Ctx = NoCtx;
+  static constexpr int NV = 1;
+  static constexpr int NRED = 0;
+  static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
+  const T* in;
+  const Xchg* X;          // shared memory
+  unsigned int seq;
+  __device__ bool begin() { return true; }
+  __device__ T gather(int col) const { return ldg(in + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int) const { return Ctx{}; }
+  __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) {
+    const int e = XCHG_TAIL + r;
+    const int s = e / X->seg;
+    ll_store(X->recv[s] + (size_t)X->rank * X->seg + (e - s * X->seg), (double)acc[0], seq);
+  }
+  __device__ void finalize(const double (&)[1]) {}
+};
+
+// ONE kernel for the column side of a sharded iteration (pdlp_shard_iterate_p2p): the K_g^T y_g SpMV whose row
+// epilogue pushes the partial sums to their owners, then xchg_reduce_rule_primal.  Persistent, co-resident grid
+// (one CTA per SM on every rank); CTAs poll only after their own pushes are out, so there is no circular wait.
+template <typename T, bool SAVE_PREV>
+__global__ void __launch_bounds__(StreamCfg<T>::NT, 1)
+shard_fused_kernel(const SellView<T> A, const Xchg* Xp, const T* y, const T* c, const T* l, const T* u, Pair<T>* xp,
+                   T* xsum, Quad<T>* X4, Scalars* S, double* partials, unsigned int* ticket) {
+  using Cfg = StreamCfg<T>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[Cfg::W][Cfg::SMAX];
+  __shared__ double s_red[Cfg::W][1];
+  __shared__ Xchg X;
+  __shared__ double sh[32];
+  __shared__ double s_rule[6];
+  __shared__ int s_int[3];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  Ring R{smem + (size_t)warp * A.nstages * A.stage_bytes, &full_bar[warp][0], A.nstages, A.stage_bytes, 0u};
+  if (lane == 0) {
+    for (int s = 0; s < R.S; ++s) mbar_init(&R.bars[s], 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  xchg_load(X, Xp);
+  __syncthreads();
+  const int gw = blockIdx.x * Cfg::W + warp;
+  const int pb = A.warp_piece_begin[gw];
+  const int pe = A.warp_piece_begin[gw + 1];
+  ring_prologue<T>(A, R, pb, pe, lane);
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const unsigned int seq = (unsigned int)S->xchg_seq;
+  if (blockIdx.x == 0 && tid == 0) {       // the step-rule partials of the previous iteration travel in the tail
+    const double t0 = S->rule_pending ? S->dy2 : 0.0, t1 = S->rule_pending ? S->inter : 0.0;
+    uint4* dst = X.recv[0] + (size_t)X.rank * X.seg;          // elements 0 .. 3 belong to rank 0's segment
+    ll_store(dst + 0, t0, seq);
+    ll_store(dst + 1, t1, seq);
+    ll_store(dst + 2, 0.0, seq);
+    ll_store(dst + 3, 0.0, seq);
+  }
+  ShardPushOp<T> op{y, &X, seq};
+  double red[1] = {0.0};
+  stream_phase<ShardPushOp<T>, 1>(A, op, red, R, pb, pe, s_red);
+  xchg_reduce_rule_primal<T, SAVE_PREV>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
 }
 
 // element-wise KKT column side on the allreduced K^T Y4 (same arithmetic as KktColsOp::row_finish); one block
@@ -1372,6 +1467,13 @@ template <typename T, int MODE>
 __global__ void vec_scale_kernel(T* v, const T* s, int len) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) v[i] = MODE == 0 ? v[i] * s[i] : v[i] / s[i];
+}
+
+// clu[j] = (c_j, l_j, u_j, 0): the constant operands of the primal epilogue in one sector
+template <typename T>
+__global__ void pack_clu_kernel(const T* c, const T* l, const T* u, Quad<T>* clu, int n) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) clu[j] = Quad<T>{{c[j], l[j], u[j], T(0)}};
 }
 
 template <typename T>

@@ -77,16 +77,6 @@ def to_device_csr(K, device: torch.device, dtype: torch.dtype):
     Kc = Kc.to(device)
     if Kc.dtype != dtype:
         Kc = Kc.to(dtype)
-    if Kc.layout == torch.strided:
-        coo = Kc.to_sparse_coo().coalesce()
-    elif Kc.layout == torch.sparse_coo:
-        coo = Kc.coalesce()
-    elif Kc.layout == torch.sparse_csr:
-        coo = Kc.to_sparse_coo().coalesce()
-    else:
-        raise TypeError(f"unsupported K layout {Kc.layout}")
-    m, n = coo.shape
-    rows, cols, vals = coo.indices()[0], coo.indices()[1], coo.values()
 
     def csr_of(r, c, v, nrows):
         counts = torch.bincount(r, minlength=nrows)
@@ -94,8 +84,32 @@ def to_device_csr(K, device: torch.device, dtype: torch.dtype):
         torch.cumsum(counts, 0, out=crow[1:])
         return crow.to(torch.int32).contiguous(), c.to(torch.int32).contiguous(), v.contiguous()
 
-    csr = csr_of(rows, cols, vals, m)                     # coalesced COO is sorted by (row, col)
-    order = torch.argsort(cols * m + rows)                # sort by (col, row): stable, unique keys
+    m, n = Kc.shape
+    csr = None
+    if Kc.layout == torch.sparse_csr:
+        # fast path: a canonical CSR (columns strictly increasing inside every row: sorted, no duplicates) is taken
+        # as it is -- no round trip through COO and no sort for K itself
+        crow, col, vals = Kc.crow_indices(), Kc.col_indices(), Kc.values()
+        nnz = int(vals.numel())
+        rows = torch.repeat_interleave(torch.arange(m, device=device), crow[1:] - crow[:-1], output_size=nnz)
+        canonical = nnz < 2 or bool(torch.all((col[1:] > col[:-1]) | (rows[1:] != rows[:-1])))
+        if canonical:
+            cols = col
+            csr = (crow.to(torch.int32).contiguous(), col.to(torch.int32).contiguous(), vals.contiguous())
+    if csr is None:
+        if Kc.layout == torch.strided:
+            coo = Kc.to_sparse_coo().coalesce()
+        elif Kc.layout == torch.sparse_coo:
+            coo = Kc.coalesce()
+        elif Kc.layout == torch.sparse_csr:
+            # (to_sparse_coo() would flag its result as coalesced without looking: build the COO from the indices)
+            coo = torch.sparse_coo_tensor(torch.stack([rows, col.to(torch.int64)]), vals, size=(m, n)).coalesce()
+        else:
+            raise TypeError(f"unsupported K layout {Kc.layout}")
+        rows, cols, vals = coo.indices()[0], coo.indices()[1], coo.values()
+        csr = csr_of(rows, cols, vals, m)                 # coalesced COO is sorted by (row, col)
+    # K^T: entries are in (row, col) order, so a STABLE sort by column alone gives (col, row) order -- 32-bit keys
+    order = torch.sort(cols.to(torch.int32), stable=True)[1]
     csc = csr_of(cols[order], rows[order], vals[order], n)
     return (m, n, int(vals.numel())), csr, csc
 
