@@ -99,6 +99,19 @@ def test_two_gpu_solve_matches_executed_reference(exchange, adaptive, pw):
 
 
 @needs_two
+def test_two_gpu_solve_in_column_windows(monkeypatch):
+    """The config-5 path at small scale: row partition over two ranks AND K_g x in column windows."""
+    monkeypatch.setenv("PDLP_WINDOW_MB", "0.008")
+    with open(os.path.join(GOLD, "cfg1_reference.json")) as f:
+        runs = json.load(f)["runs"]
+    gold = [r for r in runs if r["options"] == dict(ruiz=False, fishnet=False, adaptive=False, primal_weight=False)][0]["reference"]
+    res = run_world("nccl", False, False)
+    assert res["same_x"] and res["status"] == gold["status"]
+    assert (res["k"], res["n"], res["j"]) == (gold["k"], gold["n"], gold["j"])
+    assert abs(res["obj"] - gold["obj"]) <= 1e-9 * abs(gold["obj"])
+
+
+@needs_two
 def test_two_gpu_exchanges_agree():
     """NCCL allreduce and the fused peer-memory exchange: the same solve (fixed step: bit for bit in k / n / j)."""
     a = run_world("nccl", False, False, "mid")
