@@ -187,9 +187,7 @@ def run_engine(args):
         eng.iterate(RESTART_PERIOD, save_previous=True, use_graph=True)
         return eng.restart_check(False)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier():              # single process from here on (N > 1 went to run_sharded above)
         torch.cuda.synchronize(dev)
 
     reset()
@@ -197,8 +195,7 @@ def run_engine(args):
         step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -209,13 +206,9 @@ def run_engine(args):
     ms = e0.elapsed_time(e1)
     # per-kernel durations, CUDA events on the engine's stream (cannot be placed inside the graph replay)
     prim_ms, dual_ms = eng.time_kernels(200)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    clocks = sampler.stop()
     iters = RESTART_PERIOD * args.steps
-    value = world * iters / (ms * 1e-3)          # every rank solves its own LP (replicas): whole-job aggregate
+    value = iters / (ms * 1e-3)
 
     # ---- e2e: whole solves through the public API from pinned host tensors ----
     c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr")
@@ -246,11 +239,7 @@ def run_engine(args):
         solve_wall.append(round(time.perf_counter() - t_solve, 4))
     barrier()
     e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * e2e_iters / e2e_s
+    e2e_value = e2e_iters / e2e_s
     d2h = x_host.numel() * x_host.element_size() + 64
 
     # ---- config 4 (2M x 4M, ~50M nnz, power-law rows): hot-loop rate on the load-balance stress case ----
@@ -284,7 +273,7 @@ def run_engine(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "40 PDHG iterations + restart test (3 KKT errors)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no data-path collective)",
+                       "parallelism": "single GPU",
                        "l2": "working set 140 MB of matrix+vectors per iteration > 126 MB L2; no explicit flush",
                        "sigma_max": sigma, "bytes_per_iteration": b_iter},
             "us_per_iteration": 1e3 * ms / iters,
@@ -312,8 +301,6 @@ def run_engine(args):
             "cfg4": cfg4,
         }
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_cfg4(dev):

@@ -256,11 +256,10 @@ def test_cfg3_full_size_certificates_fire(case):
     """Config 3 at full size (100k x 200k) on LPs whose certificate tests FIRE under the reference's semantics
     (enhancements.py:106-161, call site primal_dual_hybrid_gradient.py:89-101): a contradictory pair of rows on an
     isolated variable (violation far above the termination tolerance) and a primal ray.  The oracle's full-size runs
-    (tests/golden/make_golden_large.py; 9-25 minutes of CPU each) record what the reference's heuristic returns --
+    (tests/golden/make_golden_large.py; 9-33 minutes of CPU each) record what the reference's heuristic returns --
     it tests the dual certificate first and accepts a vanishing dx, so the primal-infeasible LP is labelled
-    DUAL_INFEASIBLE and the unbounded one PRIMAL_INFEASIBLE, as on the small LPs the executed reference pins.  The
-    engine, with the tests fused into the iteration kernels, must stop with the same verdict at the same
-    iteration (fixed step: k, n, j exact)."""
+    DUAL_INFEASIBLE, as on the small LP the executed reference pins.  The engine, with the tests fused into the
+    iteration kernels, must stop with the same verdict at the same iteration (fixed step: k, n, j exact)."""
     path = os.path.join(GOLD, f"{case}_oracle.json")
     if not os.path.exists(path):
         pytest.skip(f"{case}_oracle.json not generated")
@@ -269,14 +268,17 @@ def test_cfg3_full_size_certificates_fire(case):
           else synthetic.unbounded_lp(80_000, 20_000, 200_000, 50, seed=0, name="cfg3_unbounded"))
     assert (lp.m, lp.n, lp.nnz) == (gold["lp"]["m"], gold["lp"]["n"], gold["lp"]["nnz"])
     run = gold["runs"][0]
-    assert run["status"] in ("DUAL_INFEASIBLE", "PRIMAL_INFEASIBLE")
+    # the isolated pair fires (DUAL_INFEASIBLE at k = 25 881); the primal ray does not within 100 000 KKT passes at this
+    # size (it does on the 2000 x 4000 version: PRIMAL_INFEASIBLE at k = 18 428) -- then the 48 180 iterations with the
+    # certificate sums evaluated in every one of them must give the same pass accounting and objective
+    assert run["status"] == ("DUAL_INFEASIBLE" if case == "cfg3_infeasible" else "Unsolved (KKT passes limit exceeded)")
     x, obj, k, n, j, status, secs, info = solve(lp, infeasibility_detect=True, max_kkt=100_000)
     assert status == run["status"], (status, k, run["k"])
     assert (k, n, j) == (run["k"], run["n"], run["j"]), (k, n, j, run["k"], run["n"], run["j"])
     assert rel(obj, run["obj"]) < 1e-8
-    # the verbose (host-driven) loop stops at the same iteration
-    x2, obj2, k2, n2, j2, status2, *_ = solve(lp, infeasibility_detect=True, max_kkt=100_000, verbose=True)
-    assert (status2, k2, n2, j2) == (status, k, n, j)
+    if case == "cfg3_infeasible":      # the verbose (host-driven) loop stops at the same iteration
+        x2, obj2, k2, n2, j2, status2, *_ = solve(lp, infeasibility_detect=True, max_kkt=100_000, verbose=True)
+        assert (status2, k2, n2, j2) == (status, k, n, j)
 
 
 @pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
