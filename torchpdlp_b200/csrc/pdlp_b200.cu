@@ -665,8 +665,6 @@ struct EngineT {
   struct GraphEntry { int n_iters; int save_prev; int infeas; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
   cudaGraphExec_t check_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [force][have_prev]
-  cudaGraphExec_t power_graph = nullptr;   // the rounds of the power iteration
-  int power_graph_iters = 0;
   bool check_warm[2][2] = {{false, false}, {false, false}};
   Scalars* h_scalars = nullptr;          // pinned read-back buffer
   std::vector<void*> allocs;
@@ -1030,9 +1028,11 @@ static int build_windows(EngineT<T>* E) {
   const char* env = getenv("PDLP_WINDOW_MB");
   const double window_mb = env ? atof(env) : 64.0;
   const double table_mb = (double)A.cols * sizeof(Pair<T>) / 1e6;
-  if (window_mb <= 0.0 || table_mb <= 1.5 * window_mb) return 0;
-  const int P = (int)std::ceil(table_mb / window_mb);
-  if (P < 2 || P > PANEL_MAX) return 0;
+  // a pair vector of about one window already misses L2 in 60 % of its gathers (config 4: 64 MB, measured): from
+  // 0.9 windows on the matrix is cut in at least two
+  if (window_mb <= 0.0 || table_mb <= 0.9 * window_mb) return 0;
+  const int P = std::max(2, (int)std::ceil(table_mb / window_mb));
+  if (P > PANEL_MAX) return 0;
   const int width = ((A.cols + P - 1) / P + 3) / 4 * 4;
   W.begin.assign((size_t)P + 1, A.cols);
   for (int p = 0; p < P; ++p) W.begin[p] = std::min(A.cols, p * width);
@@ -1240,7 +1240,6 @@ static void engine_destroy(pdlp_engine* B) {
   EngineT<T>* E = (EngineT<T>*)B->impl;
   if (!E) return;
   for (auto& g : E->graphs) cudaGraphExecDestroy(g.exec);
-  if (E->power_graph) cudaGraphExecDestroy(E->power_graph);
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b)
       if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
@@ -1590,39 +1589,9 @@ static int engine_power_iteration(EngineT<T>* E, const void* b0, int iters, doub
   cudaStream_t st = B->stream;
   const int n = (int)B->n;
   CU(cudaMemcpyAsync(E->tmp_n, b0, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
-  // 3 launches per round: the rounds are replayed as ONE CUDA graph (built on first use for this round count), so
-  // the 300 launches of the reference's 100 rounds (helpers.py:41-51) do not depend on the host's launch rate
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  CU(cudaStreamIsCapturing(st, &cs));
-  bool done = false;
-  if (cs == cudaStreamCaptureStatusNone && iters >= 8) {
-    if (E->power_graph && E->power_graph_iters != iters) {
-      cudaGraphExecDestroy(E->power_graph);
-      E->power_graph = nullptr;
-    }
-    if (!E->power_graph) {
-      CU((prep_kernel<SpmvOp<T, false>>()));
-      CU((prep_kernel<SpmvOp<T, true>>()));
-      cudaStream_t cap;
-      CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-      cudaGraph_t graph = nullptr;
-      CU(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-      const int rc = enqueue_power_rounds<T>(E, iters, cap);
-      const cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
-      if (!rc && e2 == cudaSuccess && cudaGraphInstantiate(&E->power_graph, graph, 0) == cudaSuccess)
-        E->power_graph_iters = iters;
-      else
-        E->power_graph = nullptr;
-      if (graph) cudaGraphDestroy(graph);
-      cudaStreamDestroy(cap);
-      cudaGetLastError();
-    }
-    if (E->power_graph) {
-      CU(cudaGraphLaunch(E->power_graph, st));
-      done = true;
-    }
-  }
-  if (!done) {
+  // (replaying the rounds as one CUDA graph was measured in round 2: capture + instantiation of the 301-node graph per
+  // engine costs more than the launch gaps it removes -- 10.2 ms against 9.0 ms for the reference's 100 rounds)
+  {
     const int rc = enqueue_power_rounds<T>(E, iters, st);
     if (rc) return rc;
   }
