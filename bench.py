@@ -30,6 +30,9 @@ METRIC = "pdhg_iterations_per_sec"
 UNIT = "it/s"
 WORKLOAD = "cfg2: synthetic bounded LP m=100000 n=200000 nnz=5000000 (50/row), fp64, restarts + adaptive step + primal weight"
 RESTART_PERIOD = 40
+# the same `config` on both arms (engine and --impl reference): the reference arm times a bounded sample of this step
+CONFIG_N1 = {"workload": WORKLOAD, "step": "40 PDHG iterations + restart test (3 KKT errors)", "parallelism": "single GPU",
+             "l2": "working set 140 MB of matrix+vectors per iteration > 126 MB L2; no explicit flush"}
 KERNELS_PER_STEP = 2 * RESTART_PERIOD + 6      # 80 iteration kernels + flush, 2 KKT, decide, apply, post
 
 
@@ -146,8 +149,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": f"{per_step} adaptive PDHG iterations (bounded sample)",
-                   "layout": "torch sparse COO (reference layout)"},
+        "config": dict(CONFIG_N1),
+        "sample_step": f"{per_step} adaptive PDHG iterations per step (bounded sample of the step in `config`), K as torch sparse "
+                       "COO (the reference's sparse layout)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} x {per_step} adaptive iterations of the oracle port, torch sparse COO, "
                                    f"{cores} threads of {os.cpu_count()} cpus; same port on torch sparse CSR (MKL): {csr:.1f} it/s"},
@@ -272,10 +276,8 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": "40 PDHG iterations + restart test (3 KKT errors)",
-                       "parallelism": "single GPU",
-                       "l2": "working set 140 MB of matrix+vectors per iteration > 126 MB L2; no explicit flush",
-                       "sigma_max": sigma, "bytes_per_iteration": b_iter},
+            "config": dict(CONFIG_N1),
+            "sigma_max": sigma, "bytes_per_iteration": b_iter,
             "us_per_iteration": 1e3 * ms / iters,
             "iteration_roofline_frac": b_iter / (ms * 1e-3 / iters) / 1e9 / peak,
             "time_to_tolerance": {"rel_kkt": 1e-4, "iterations": e2e_iters // n_solves, "status": status,
