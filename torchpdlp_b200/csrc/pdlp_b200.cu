@@ -1334,7 +1334,7 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   cudaStream_t st = B->stream;
   if (n_iters <= 0) return 0;
   if (save_prev) B->have_prev = true;
-  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0) {
+  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0 && !E->win.on) {
     // one persistent cooperative kernel for the whole block (SELL layout only; otherwise the CUDA graph below)
     const int grid = std::max(E->K.grid, E->Kt.grid);
     const int stages = std::min(E->K.nstages, E->Kt.nstages);
@@ -1777,7 +1777,8 @@ static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
 // ---- peer-memory exchange: one iteration = SpMV -> exchange kernel -> rule -> primal (polls) -> dual ----
 static int xchg_seg(int L, int world) { return ((L + world - 1) / world + 1) / 2 * 2; }
 static size_t xchg_block_bytes(int L, int world) {
-  return sizeof(double) * (size_t)L + 16 * ((size_t)world * xchg_seg(L, world) + (size_t)L);
+  // part | recv | tot | (two ranks) the one-shot slots: 2 parities x 2 ranks x L words
+  return sizeof(double) * (size_t)L + 16 * ((size_t)world * xchg_seg(L, world) + (size_t)L + (world == 2 ? 4 * (size_t)L : 0));
 }
 
 // unmap the peers' blocks (every rank does this, then a host barrier, before any rank frees its own block)
@@ -1840,6 +1841,11 @@ static int xchg_connect(EngineT<T>* E, const unsigned char* handles) {
     }
     X.recv[p] = (uint4*)(base + sizeof(double) * (size_t)L);
     X.tot[p] = X.recv[p] + (size_t)world * seg;
+    X.os[p] = X.tot[p] + (size_t)L;
+  }
+  {
+    const char* v = getenv("PDLP_XCHG_ONESHOT");      // developer knob: 0 keeps the two-shot protocol with two ranks
+    X.oneshot = (world == 2 && !(v && v[0] == '0')) ? 1 : 0;
   }
   X.part = (double*)B->xchg_block;
   X.world = world;

@@ -694,6 +694,10 @@ __global__ void shard_rule_kernel(Scalars* S, const double* tail) {
 //                        of every rank (NVLink stores), evaluates the step rule from the tail and updates x as its
 //                        share of tot[] arrives (xchg_reduce_rule_primal).
 //   xchg_allreduce_kernel  the same two phases for a caller's buffer (restart test, power iteration).
+// With TWO ranks the fused kernel uses a one-shot variant instead (same bytes on the wire, one NVLink hop less): each
+// rank stores its partial sums into its slot on BOTH ranks and every rank adds the two slots itself, in rank order.  The
+// slots are double-buffered by the parity of seq: a rank can run at most one exchange ahead of its peer (it needs the
+// peer's pushes of exchange s + 1 to finish s + 1), so slot (s & 1) is rewritten only after the peer has read it.
 // Each segment is summed by exactly one rank, so all ranks see bit-identical totals.  The grid of xchg_kernel is
 // co-resident (phase 2 of one GPU waits for phase 1 of the others, never for its own later CTAs).  A poll that
 // lasts longer than XCHG_TIMEOUT_NS sets Scalars::xchg_error + stop instead of hanging the GPU.
@@ -704,10 +708,11 @@ constexpr unsigned long long XCHG_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000u
 struct Xchg {
   uint4* recv[MAX_PEERS];      // every rank's recv area (world x seg words)
   uint4* tot[MAX_PEERS];       // every rank's tot area (L words)
+  uint4* os[MAX_PEERS];        // one-shot exchange (two ranks): every rank's 2 parities x 2 slots x L words
   double* part;                // this rank's partial vector
   int world, rank;
   int L, seg;                  // padded length, elements per segment
-  int n, pad;
+  int n, oneshot;
 };
 
 __device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
@@ -883,18 +888,26 @@ __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, c
 // (read-only on Scalars), polls its share of tot[] and updates x; the last CTA -- every reader of Scalars is done by
 // then -- commits the rule, ||dx||^2 and the sequence number.  The grid must be co-resident.  sh: >= blockDim / 32
 // doubles, s_rule: 6 doubles, s_int: 3 ints of shared memory.
-template <typename T, bool SAVE_PREV>
+template <typename T, bool SAVE_PREV, bool ONESHOT>
 __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned int seq, const T* c, const T* l, const T* u,
                                                         Pair<T>* xp, T* xsum, Quad<T>* X4, Scalars* S, double* partials,
                                                         unsigned int* ticket, double* sh, double* s_rule, int* s_int) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthr = gridDim.x * blockDim.x;
-  xchg_reduce_owned(X, X.L, seq, S, tid, nthr);
-  const uint4* tot = X.tot[X.rank];
+  if (!ONESHOT) xchg_reduce_owned(X, X.L, seq, S, tid, nthr);
+  // two-shot: the totals arrive in tot[]; one-shot (two ranks): both ranks' partial vectors arrive in this rank's two
+  // slots of parity seq & 1 and are added here, in rank order, by every rank for itself (same bits on both)
+  const uint4* tot = ONESHOT ? X.os[X.rank] + (size_t)((seq & 1u) * 2u) * X.L : X.tot[X.rank];
+  const uint4* tot1 = tot + X.L;          // one-shot: rank 1's slot
   if (threadIdx.x == 0) {
     const uint4 v0 = ll_load(tot + 0), v1 = ll_load(tot + 1);
-    const double dy2 = ll_wait(tot + 0, seq, S, v0);
-    const double inter = ll_wait(tot + 1, seq, S, v1);
+    double dy2 = ll_wait(tot + 0, seq, S, v0);
+    double inter = ll_wait(tot + 1, seq, S, v1);
+    if (ONESHOT) {
+      const uint4 w0 = ll_load(tot1 + 0), w1 = ll_load(tot1 + 1);
+      dy2 = dy2 + ll_wait(tot1 + 0, seq, S, w0);
+      inter = inter + ll_wait(tot1 + 1, seq, S, w1);
+    }
     const int pending = S->rule_pending;
     double eta = S->eta, wp = S->w_pending, w = 0.0, next = 0.0;
     if (pending) {
@@ -913,9 +926,10 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
     const T tau = (T)(s_rule[0] / S->omega);
     const T wpend = (T)s_rule[1];
     const uint4* col = tot + XCHG_TAIL;
+    const uint4* col1 = tot1 + XCHG_TAIL;
     constexpr int NB = 4;
     for (int j0 = tid; j0 < X.n; j0 += NB * nthr) {
-      uint4 v[NB];
+      uint4 v[NB], w[ONESHOT ? NB : 1];
       T cj[NB], lj[NB], uj[NB], sj[NB];
       Pair<T> pj[NB];
 #pragma unroll
@@ -923,6 +937,7 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
         const int j = j0 + b * nthr;
         if (j < X.n) {
           v[b] = ll_load(col + j);
+          if (ONESHOT) w[ONESHOT ? b : 0] = ll_load(col1 + j);
           cj[b] = c[j]; lj[b] = l[j]; uj[b] = u[j]; sj[b] = xsum[j]; pj[b] = xp[j];
         }
       }
@@ -930,7 +945,9 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
       for (int b = 0; b < NB; ++b) {
         const int j = j0 + b * nthr;
         if (j < X.n) {
-          const T g = cj[b] - (T)ll_wait(col + j, seq, S, v[b]);
+          double kty = ll_wait(col + j, seq, S, v[b]);
+          if (ONESHOT) kty = (0.0 + kty) + ll_wait(col1 + j, seq, S, w[ONESHOT ? b : 0]);     // rank order, as the owner sums
+          const T g = cj[b] - (T)kty;
           const T xo = pj[b].a;
           const T xn = clampv(xo - tau * g, lj[b], uj[b]);
           const T dx = xn - xo;
@@ -996,6 +1013,12 @@ struct ShardPushOp {
   __device__ Ctx row_load(int) const { return Ctx{}; }
   __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&)[1]) {
     const int e = XCHG_TAIL + r;
+    if (X->oneshot) {         // two ranks: the partial sum goes to this rank's slot on BOTH ranks
+      const size_t off = (size_t)((seq & 1u) * 2u + (unsigned)X->rank) * X->L + e;
+      ll_store(X->os[0] + off, (double)acc[0], seq);
+      ll_store(X->os[1] + off, (double)acc[0], seq);
+      return;
+    }
     const int s = e / X->seg;
     ll_store(X->recv[s] + (size_t)X->rank * X->seg + (e - s * X->seg), (double)acc[0], seq);
   }
@@ -1039,16 +1062,22 @@ shard_fused_kernel(const SellView<T> A, const Xchg* Xp, const T* y, const T* c, 
   const unsigned int seq = (unsigned int)S->xchg_seq;
   if (blockIdx.x == 0 && tid == 0) {       // the step-rule partials of the previous iteration travel in the tail
     const double t0 = S->rule_pending ? S->dy2 : 0.0, t1 = S->rule_pending ? S->inter : 0.0;
-    uint4* dst = X.recv[0] + (size_t)X.rank * X.seg;          // elements 0 .. 3 belong to rank 0's segment
-    ll_store(dst + 0, t0, seq);
-    ll_store(dst + 1, t1, seq);
-    ll_store(dst + 2, 0.0, seq);
-    ll_store(dst + 3, 0.0, seq);
+    for (int p = 0; p < (X.oneshot ? 2 : 1); ++p) {
+      uint4* dst = X.oneshot ? X.os[p] + (size_t)((seq & 1u) * 2u + (unsigned)X.rank) * X.L
+                             : X.recv[0] + (size_t)X.rank * X.seg;      // elements 0 .. 3 belong to rank 0's segment
+      ll_store(dst + 0, t0, seq);
+      ll_store(dst + 1, t1, seq);
+      ll_store(dst + 2, 0.0, seq);
+      ll_store(dst + 3, 0.0, seq);
+    }
   }
   ShardPushOp<T> op{y, &X, seq};
   double red[1] = {0.0};
   stream_phase<ShardPushOp<T>, 1>(A, op, red, R, pb, pe, s_red);
-  xchg_reduce_rule_primal<T, SAVE_PREV>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
+  if (X.oneshot)
+    xchg_reduce_rule_primal<T, SAVE_PREV, true>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
+  else
+    xchg_reduce_rule_primal<T, SAVE_PREV, false>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
 }
 
 // element-wise KKT column side on the allreduced K^T Y4 (same arithmetic as KktColsOp::row_finish); one block
