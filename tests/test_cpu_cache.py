@@ -78,3 +78,21 @@ def test_engine_for_matrix_reuses_any_engine_of_that_matrix(monkeypatch):
     e2 = _cache.engine_for_matrix(K2)
     assert e2 is not e and _cache.engine_for_matrix(K2) is e2 and FakeEngine.built == 2
     _cache.clear()
+
+
+def test_numpy_and_scipy_sources_are_fingerprinted(monkeypatch):
+    """numpy / scipy inputs have no version counter: an in-place edit is caught by the content fingerprint."""
+    import numpy as np
+    import scipy.sparse as sp
+    monkeypatch.setattr(_cache, "Engine", FakeEngine)
+    _cache.clear()
+    K = sp.random(8, 12, density=0.4, format="csr", random_state=np.random.default_rng(0))
+    c, q, l, u = np.ones(12), np.arange(8.0), np.zeros(12), np.full(12, 5.0)
+    e1 = _cache.engine_for(K, 3, c, q, l, u)
+    assert _cache.engine_for(K, 3, c, q, l, u) is e1
+    q[2] += 1.0
+    e2 = _cache.engine_for(K, 3, c, q, l, u)
+    assert e2 is not e1
+    K.data[0] *= 2.0
+    assert _cache.engine_for(K, 3, c, q, l, u) is not e2
+    _cache.clear()

@@ -19,6 +19,7 @@ from __future__ import annotations
 import weakref
 from collections import OrderedDict
 
+import numpy as np
 import torch
 
 from .engine import Engine
@@ -38,9 +39,19 @@ def _payload(t):
     return t
 
 
-def _version(t) -> int:
+def _version(t):
+    """What changes when the data of ``t`` is edited in place: torch's version counter; for numpy arrays and scipy
+    matrices (no counter) a content fingerprint -- the sum of all values and of every other value, O(size) per
+    lookup (a few milliseconds for the 5M values of config 2, once per solve)."""
     p = _payload(t)
-    return int(p._version) if isinstance(p, torch.Tensor) else 0
+    if isinstance(p, torch.Tensor):
+        return int(p._version)
+    data = p if isinstance(p, np.ndarray) else getattr(p, "data", None)      # scipy sparse: the values array
+    if isinstance(data, np.ndarray) and data.size:
+        flat = data.reshape(-1)
+        with np.errstate(all="ignore"):
+            return (flat.size, float(np.sum(flat, dtype=np.float64)), float(np.sum(flat[::2], dtype=np.float64)))
+    return 0
 
 
 class _Snap:
