@@ -63,6 +63,8 @@ def run_restart_loop(engine: Engine, max_kkt, restart_period, time_limit, time_u
     status = _BOUND
     prim_obj = float("nan")
     trace = []
+    if hasattr(engine, "timeout_probe"):       # row-partitioned: the flag rides in the restart test's last collective
+        engine.timeout_probe = lambda: time.time() - t_start + time_used >= time_limit
     while j < max_kkt:
         t = 0
         restarted = False

@@ -192,7 +192,9 @@ class ShardedSolver:
         self.buf3 = prims.buffer(3 * n)
         self.buf9 = prims.buffer(9)
         self.buf4 = prims.buffer(4)
-        self.buf1 = prims.buffer(1)
+        self.buf1 = prims.buffer(2)                                 # [||y_restart - y_last||^2 partial, time-limit flag]
+        self.timeout_probe = None                                  # set by the restart loop: () -> bool, this rank's clock
+        self._agreed_timeout = None
         self.collectives = 0
         self._graphs = {}
         self._have_prev = False
@@ -272,18 +274,46 @@ class ShardedSolver:
         if save_previous:
             self._have_prev = True
 
-    def restart_check(self, force: bool = False):
+    def _check_enqueue(self, force: bool, have_prev: bool):
+        """Everything of the restart test up to its last collective: device work and collectives only, no host
+        round trip -- capturable."""
         self.p.rule_pack(self.buf4)                                # step rule of the block's last iteration
         self._allreduce(self.buf4)
         self.p.rule_apply(self.buf4)
-        self.p.check_begin(self.buf3, self._have_prev and not force)
-        self._have_prev = False
+        self.p.check_begin(self.buf3, have_prev)
         self._allreduce(self.buf3)                                 # K^T y of current / average / previous iterate
         self.p.check_mid(self.buf3, self.buf9)
         self._allreduce(self.buf9)                                 # row-side KKT sums
-        self.p.check_decide(self.buf9, force, self.buf1)
-        self._allreduce(self.buf1)                                 # ||y_restart - y_last||^2
-        return self.p.check_end(self.buf1)
+        self.p.check_decide(self.buf9, force, self.buf1)           # buf1[0] = this rank's ||y_restart - y_last||^2
+        self._allreduce(self.buf1)                                 # ... and buf1[1] = time-limit flags (see below)
+
+    def restart_check(self, force: bool = False):
+        """The restart test (primal_dual_hybrid_gradient.py:115-177): four collectives between the device stages.
+        From the second use on the whole sequence is replayed as ONE CUDA graph per (force, have_prev) pair, like the
+        iteration blocks, so its ~20 launches do not wait for the host.  The last collective also carries every
+        rank's "my clock says the time limit is reached" flag (``timeout_probe``, set by the restart loop), so the
+        collective time-limit decision of the NEXT block costs neither a collective nor a host round trip."""
+        have_prev = bool(self._have_prev and not force)
+        self._have_prev = False
+        flag = 1.0 if (self.timeout_probe is not None and self.timeout_probe()) else 0.0
+        self.buf1[1] = flag                                        # stream-ordered before the graph / the eager launches
+        key = ("check", bool(force), have_prev)
+        state = self._graphs.get(key)
+        if hasattr(self.p, "capture_block") and state is not None:
+            if state == "warm":
+                before = self.collectives
+                state = self.p.capture_block(lambda: self._check_enqueue(force, have_prev))
+                self.collectives = before
+                self._graphs[key] = state
+            state()
+            self.collectives += 4
+        else:
+            if hasattr(self.p, "capture_block"):
+                self._graphs[key] = "warm"                         # first use runs eagerly (kernel attributes, channels)
+            self._check_enqueue(force, have_prev)
+        chk = self.p.check_end(self.buf1)                          # the one host round trip of the test
+        self._agreed_timeout = bool(float(self.buf1[1].item()) > 0.5) if self.timeout_probe is not None else None
+        return chk
 
     def state(self):
         return self.p.state()
@@ -294,6 +324,9 @@ class ShardedSolver:
         waiting in the next exchange.  So the limit is reached when ANY rank has reached it (a sum over ranks of
         the 0/1 flags, through the same exchange as every other collective), and all ranks stop in the same
         block."""
+        if self._agreed_timeout is not None:                       # agreed on in the last restart test's collective
+            agreed, self._agreed_timeout = self._agreed_timeout, None
+            return agreed
         if self.world <= 1 and not self._p2p_ready:
             return bool(timed_out)
         t = torch.tensor([1.0 if timed_out else 0.0], dtype=torch.float64, device=self.buf.device)
