@@ -190,6 +190,27 @@ def test_sharded_peer_exchange_single_rank(adaptive, pw, cfg1):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_sharded_short_row_transpose_uses_the_run_layout(monkeypatch):
+    """A row block of a much larger LP has very short rows in K_g^T; pdlp_shard_kty then multiplies on the run layout
+    (rule in engine_create, forced here through PDLP_KT_RUN_MIN_NNZ on an LP with 4 entries per row of K^T).  Same solve
+    as without it: fixed step, equal k / n / j, objective to 1e-9."""
+    from torchpdlp_b200.sharded import build_rank_engine
+    torch.set_default_dtype(torch.float64)
+    lp = synthetic.uniform_rows_lp(1600, 400, 10_000, 20, seed=2, name="short_rows")      # K^T: 10 000 rows of ~4 entries
+    outs = []
+    for knob in (None, "0"):
+        if knob is None:
+            monkeypatch.delenv("PDLP_KT_RUN_MIN_NNZ", raising=False)
+        else:
+            monkeypatch.setenv("PDLP_KT_RUN_MIN_NNZ", knob)
+        solver = build_rank_engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u, exchange="nccl")
+        torch.manual_seed(0)
+        x, y, obj, k, n, j, status, secs, sigma = solver.solve(max_kkt=4000)
+        outs.append((obj, k, n, j, status))
+        solver.close()
+    assert outs[0][1:] == outs[1][1:] and rel(outs[0][0], outs[1][0]) < 1e-9, outs
+
+
 @pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
 def test_sharded_entry_points_single_rank(adaptive, pw, cfg1):
     """The pdlp_shard_* kernels (partial SpMV -> [allreduce] -> element-wise epilogues, deferred step

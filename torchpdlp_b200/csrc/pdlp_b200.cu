@@ -1184,7 +1184,14 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
     if (rc) return rc;
     if (!E->Kt.run_on) E->k1 = 0;
   }
-  if (E->k1 == 1 || E->k2 == 1) tr.lap("run layout");
+  const char* kt_env = getenv("PDLP_KT_RUN_MIN_NNZ");       // developer / test knob: smallest nnz for this rule
+  if (E->k1 != 1 && nnz >= (kt_env ? atoll(kt_env) : 10000000LL) && (double)nnz <= 8.0 * (double)n) {
+    // very short rows of K^T (a row block of a much larger LP): the plain K_g^T y_g product of the row-partitioned
+    // engine (pdlp_shard_kty) runs faster on the run layout; the fused PrimalOp keeps SELL
+    rc = build_run<T>(E, E->Kt);
+    if (rc) return rc;
+  }
+  if (E->k1 == 1 || E->k2 == 1 || E->Kt.run_on) tr.lap("run layout");
   rc = build_windows<T>(E);
   if (rc) return rc;
   if (E->k1 == 2) {
@@ -1203,7 +1210,10 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   CU(cudaMemsetAsync(E->kty_old, 0, sizeof(T) * n, st));
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
   ALLOC(E->S, 1);
-  E->ew_grid = B->sms * 2;
+  // element-wise kernels (restart, sharded primal update): 2 CTAs of 256 threads per SM, up to 8 per SM for vectors long
+  // enough to be bandwidth-bound (config 5: n = 40M; measured 0.78 ms for the 3.2 GB of the sharded primal update
+  // with 2 per SM)
+  E->ew_grid = (int)std::min<int64_t>((int64_t)B->sms * 8, std::max<int64_t>((int64_t)B->sms * 2, std::max<int64_t>(n, m) / 2048));
   E->h_scalars = (Scalars*)pinned_scalars_get();
   if (!E->h_scalars) return fail(PDLP_ERR_CUDA, "cudaMallocHost failed");
   ALLOC(E->ew_partials, 2 * E->ew_grid);
@@ -1748,7 +1758,11 @@ static int shard_kty(EngineT<T>* E, double* buf) {
   pdlp_engine* B = E->base;
   if (sizeof(T) != sizeof(double)) return fail(PDLP_ERR_INVALID, "the sharded engine is fp64 only");
   SpmvOp<T, false> f{E->y, (T*)buf, E->S, 6};
-  CU(launch_stream(E->Kt, f, B->stream));
+  // K_g^T in the run layout when it is there: PDLP_LAYOUT=run, or rows so short that SELL's per-slice cost and slot
+  // padding dominate (config 5 over 2 / 4 / 8 GPUs: 6.3 / 3.1 / 1.6 entries per row: 1.76 -> 1.70, 0.77 -> 0.65,
+  // 0.54 -> 0.45 ms)
+  if (E->Kt.run_on) CU(launch_run(E->Kt, f, B->stream));
+  else CU(launch_stream(E->Kt, f, B->stream));
   shard_tail_pack_kernel<<<1, 1, 0, B->stream>>>(E->S, buf + B->n);
   CU(cudaGetLastError());
   return 0;
