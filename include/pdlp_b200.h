@@ -42,7 +42,8 @@ enum pdlp_status {
   PDLP_OK = 0,
   PDLP_ERR_INVALID = 1, /* bad argument */
   PDLP_ERR_CUDA = 2,    /* CUDA runtime error (message has the cudaError string) */
-  PDLP_ERR_STATE = 3    /* call sequence error (e.g. restart check before any iteration) */
+  PDLP_ERR_STATE = 3,   /* call sequence error (e.g. restart check before any iteration) */
+  PDLP_ERR_NOT_CANONICAL = 4 /* pdlp_create_host: unsorted or duplicate column indices inside a row (coalesce first) */
 };
 
 /* Restart kinds reported by pdlp_restart_check (reference
@@ -163,6 +164,17 @@ int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ine
                 const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
                 const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals,
                 const void* c, const void* q, const void* l, const void* u, void* stream);
+/* The same engine from a HOST CSR of K alone (pinned memory gives asynchronous copies; pageable works): what the
+ * reference spreads over K.to(device) at its call sites (PDLP/main.py -> primal_dual_hybrid_gradient.py:7) and the
+ * sparse conversions of PDLP/util.py:239-269.  host_K_rowptr / host_K_colidx hold index_bytes = 4 or 8 byte signed
+ * integers (torch's crow_indices / col_indices are int64), host_K_vals values of `dtype`.  The library copies the
+ * arrays to the device, narrows the indices to int32, checks the canonical form (columns strictly increasing inside
+ * every row: PDLP_ERR_NOT_CANONICAL otherwise), builds the CSR of K^T on the device (column histogram, scan, stable
+ * radix sort by column) and plans both layouts on the host while the copies and the transposition run.
+ * c, q, l, u may be host or device pointers (unified addressing decides).  Synchronises `stream`.            */
+int pdlp_create_host(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                     const void* host_K_rowptr, const void* host_K_colidx, int32_t index_bytes,
+                     const void* host_K_vals, const void* c, const void* q, const void* l, const void* u, void* stream);
 int pdlp_destroy(pdlp_handle h);
 /* Redirect the engine's work to another stream of the same device (e.g. the capture stream of a
  * CUDA graph that also holds the NCCL allreduce of the sharded loop).  The caller orders the streams. */
@@ -240,6 +252,8 @@ int pdlp_set_scaling(pdlp_handle h, const void* D_row, const void* D_col);
 int pdlp_get_problem(pdlp_handle h, void* c, void* q, void* l, void* u);
 /* Current (possibly scaled) values of K in the caller's CSR order (nnz values). */
 int pdlp_get_matrix_values(pdlp_handle h, void* K_vals);
+/* Structure of K as the engine holds it (m + 1 row pointers, nnz column indices, int32, device); either may be NULL. */
+int pdlp_get_matrix_structure(pdlp_handle h, int32_t* K_rowptr, int32_t* K_colidx);
 
 /* ---- fishnet start-point search (spectral_casting.py), 8 points per call -------------
  * X8: n x 8 and Y8: m x 8 values, point index fastest (row j holds the 8 points' j-th entry,

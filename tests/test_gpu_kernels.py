@@ -362,3 +362,90 @@ def test_fp32_engine_matches_fp32_oracle(cfg1):
         eng.close()
     finally:
         torch.set_default_dtype(torch.float64)
+
+
+def _same_engine_matrices(a, b, lp):
+    """Two engines hold bit-identical K and K^T: structure, values, and both products on random vectors."""
+    rng = np.random.default_rng(11)
+    v, w = rng.normal(size=lp.n), rng.normal(size=lp.m)
+    Ma, Mb = a.matrix().cpu(), b.matrix().cpu()
+    assert torch.equal(Ma.crow_indices(), Mb.crow_indices()) and torch.equal(Ma.col_indices(), Mb.col_indices())
+    assert torch.equal(Ma.values(), Mb.values())
+    assert torch.equal(a.spmv(v).cpu(), b.spmv(v).cpu())
+    assert torch.equal(a.spmv(w, transpose=True).cpu(), b.spmv(w, transpose=True).cpu())
+
+
+@pytest.mark.parametrize("which", ["cfg1", "ragged"])
+def test_host_ingest_equals_device_ingest(which, cfg1, monkeypatch):
+    """pdlp_create_host (H2D + canonical check + device-side transpose in the library) builds the same engine as
+    pdlp_create fed by the torch conversions: scipy int32 / torch int64 host CSR, pinned or pageable, fp64 and fp32."""
+    from torchpdlp_b200.engine import Engine
+    lp = cfg1 if which == "cfg1" else ragged_lp()
+    args = (lp.m_ineq, lp.c, lp.q, lp.l, lp.u)
+    host = Engine(lp.K, *args)
+    assert host.ingest == "host"
+    c, K, q, m_ineq, l, u = lp.torch_tensors(layout="csr", device="cuda")
+    dev = Engine(K, m_ineq, c, q, l, u)
+    assert dev.ingest == "device"
+    _same_engine_matrices(host, dev, lp)
+    # the products also agree with scipy (fp64: fixed summation order per row, so only rounding of the order differs)
+    v = np.random.default_rng(1).normal(size=lp.n)
+    np.testing.assert_allclose(host.spmv(v).cpu().numpy(), lp.K @ v, rtol=1e-12, atol=1e-12)
+    # torch CPU CSR with int64 indices in pinned memory, vectors on the host
+    ch, Kh, qh, _, lh, uh = lp.torch_tensors(layout="csr")
+    Kp = torch.sparse_csr_tensor(Kh.crow_indices().pin_memory(), Kh.col_indices().pin_memory(), Kh.values().pin_memory(),
+                                 size=Kh.shape)
+    pinned = Engine(Kp, m_ineq, ch, qh, lh, uh, device="cuda")
+    assert pinned.ingest == "host"
+    _same_engine_matrices(pinned, dev, lp)
+    for got, want in zip(pinned.problem(), dev.problem()):
+        assert torch.equal(got, want)
+    # fp32 engine from the fp64 host matrix
+    h32, d32 = Engine(lp.K, *args, dtype=torch.float32), Engine(K.to(torch.float32), m_ineq, c, q, l, u, dtype=torch.float32)
+    assert h32.ingest == "host"
+    assert torch.equal(h32.spmv(v).cpu(), d32.spmv(v).cpu())
+    # switch: PDLP_HOST_INGEST=0 sends host matrices through the torch conversions
+    monkeypatch.setenv("PDLP_HOST_INGEST", "0")
+    off = Engine(lp.K, *args)
+    assert off.ingest == "device"
+    _same_engine_matrices(off, dev, lp)
+    for e in (host, dev, pinned, h32, d32, off):
+        e.close()
+
+
+def test_host_ingest_rejects_and_falls_back(cfg1):
+    """Unsorted columns and duplicate entries are not canonical CSR: the library says so (PDLP_ERR_NOT_CANONICAL) and
+    the engine coalesces through the general path; a column outside [0, n) is an error on both."""
+    from torchpdlp_b200 import _lib
+    from torchpdlp_b200.engine import Engine
+    lp = cfg1
+    args = (lp.m_ineq, lp.c, lp.q, lp.l, lp.u)
+    ref = Engine(lp.K, *args)
+    K = lp.K.copy()
+    indptr, indices, data = K.indptr.copy(), K.indices.copy(), K.data.copy()
+    for r in range(0, lp.m, 3):                     # reverse the entries of every third row
+        b, e = indptr[r], indptr[r + 1]
+        indices[b:e], data[b:e] = indices[b:e][::-1].copy(), data[b:e][::-1].copy()
+    shuffled = (torch.from_numpy(indptr.astype(np.int64)), torch.from_numpy(indices.astype(np.int64)),
+                torch.from_numpy(data), K.shape)
+    eng = Engine(shuffled, *args)
+    assert eng.ingest == "device"
+    _same_engine_matrices(eng, ref, lp)
+    eng.close()
+    # duplicates: every entry split in two halves (first row only gets a real duplicate pair)
+    b, e = indptr[0], indptr[1]
+    assert e - b >= 1
+    dup_ptr = K.indptr.astype(np.int64).copy()
+    dup_ptr[1:] += 1
+    dup_idx = np.concatenate([K.indices[:b + 1], K.indices[b:]]).astype(np.int64)
+    dup_val = np.concatenate([K.data[:b + 1] * 0.25, [K.data[b] * 0.75], K.data[b + 1:]])
+    eng = Engine((torch.from_numpy(dup_ptr), torch.from_numpy(dup_idx), torch.from_numpy(dup_val), K.shape), *args)
+    assert eng.ingest == "device" and eng.nnz == lp.nnz
+    v = np.random.default_rng(2).normal(size=lp.n)
+    np.testing.assert_allclose(eng.spmv(v).cpu().numpy(), ref.spmv(v).cpu().numpy(), rtol=1e-13, atol=1e-13)
+    eng.close()
+    bad = K.indices.astype(np.int64).copy()
+    bad[5] = lp.n + 3
+    with pytest.raises(_lib.PdlpError, match="outside"):
+        Engine((torch.from_numpy(K.indptr.astype(np.int64)), torch.from_numpy(bad), torch.from_numpy(K.data), K.shape), *args)
+    ref.close()

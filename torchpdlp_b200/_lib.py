@@ -72,6 +72,7 @@ SYMBOLS = {
     "pdlp_last_error": (C.c_char_p, []),
     "pdlp_bytes_per_iteration": (_L, [_P]),
     "pdlp_create": (_I, [C.POINTER(_P), _I, _L, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pdlp_create_host": (_I, [C.POINTER(_P), _I, _L, _L, _L, _L, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "pdlp_destroy": (_I, [_P]),
     "pdlp_set_stream": (_I, [_P, _P]),
     "pdlp_set_iterate": (_I, [_P, _P, _P]),
@@ -94,6 +95,7 @@ SYMBOLS = {
     "pdlp_set_scaling": (_I, [_P, _P, _P]),
     "pdlp_get_problem": (_I, [_P, _P, _P, _P, _P]),
     "pdlp_get_matrix_values": (_I, [_P, _P]),
+    "pdlp_get_matrix_structure": (_I, [_P, _P, _P]),
     "pdlp_batch_spmv": (_I, [_P, _P, _P]),
     "pdlp_batch_step": (_I, [_P, _P, _P, _P, _D, _D]),
     "pdlp_batch_gap": (_I, [_P, _P, _P, C.POINTER(_D)]),
@@ -158,9 +160,14 @@ def lib() -> C.CDLL:
 
 
 class PdlpError(RuntimeError):
-    pass
+    code = 0
+
+
+ERR_NOT_CANONICAL = 4
 
 
 def check(rc: int) -> None:
     if rc != 0:
-        raise PdlpError(f"pdlp_b200 error {rc}: {lib().pdlp_last_error().decode()}")
+        err = PdlpError(f"pdlp_b200 error {rc}: {lib().pdlp_last_error().decode()}")
+        err.code = rc
+        raise err

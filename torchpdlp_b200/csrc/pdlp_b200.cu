@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "../../include/pdlp_b200.h"
 #include "pdlp_block.cuh"
 #include "pdlp_ops.cuh"
@@ -652,7 +655,7 @@ struct EngineT {
   T *y = nullptr, *xsum = nullptr, *ysum = nullptr, *xlast = nullptr, *ylast = nullptr;
   Quad<T>*X4 = nullptr, *Y4 = nullptr;
   T *drow = nullptr, *dcol = nullptr;     // accumulated scalings (ones until pdlp_ruiz)
-  T *tmp_n = nullptr, *tmp_m = nullptr, *tmp_n2 = nullptr;
+  T *tmp_n = nullptr, *tmp_m = nullptr;
   T *kty_old = nullptr, *lam_prev = nullptr;   // infeasibility detection state
   Scalars* S = nullptr;
   double* ew_partials = nullptr;
@@ -1103,6 +1106,45 @@ static int build_windows(EngineT<T>* E) {
   return 0;
 }
 
+// SELL plan of a matrix from the host copy of its row pointers (host work only) + the ring geometry that follows from it
+template <typename T>
+static HostSell plan_csr(EngineT<T>* E, DeviceCsr<T>& A) {
+  using Cfg = StreamCfg<T>;
+  HostSell P = build_sell_plan(A.h_rowptr.data(), A.rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW,
+                               PDLP_WARP_ROW, E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
+  // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows
+  A.stage_bytes = (P.max_piece_bytes + 127) / 128 * 128;
+  A.nstages = std::max(2, std::min(Cfg::SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)Cfg::W * A.stage_bytes))));
+  A.smem_bytes = Cfg::W * A.nstages * A.stage_bytes + 128;
+  A.grid = P.grid;
+  A.npieces = (int)P.pieces.size();
+  A.nlong = (int)P.long_rows.size();
+  A.packed_bytes = P.packed_bytes;
+  return P;
+}
+
+// device side of a plan: allocate the packed copy, upload the plan, fill the packed copy from the CSR master copy.
+// Asynchronous on the engine's stream; the caller synchronises before P goes out of scope.
+template <typename T>
+static int upload_plan_and_pack(EngineT<T>* E, DeviceCsr<T>& A, const HostSell& P) {
+  cudaStream_t st = E->base->stream;
+  if (P.packed_bytes / 16 >= 0xffffffffull) return fail(PDLP_ERR_INVALID, "packed matrix exceeds 64 GiB");
+  ALLOC(A.packed, P.packed_bytes + 16);
+  ALLOC(A.pieces, P.pieces.size() + 1);
+  ALLOC(A.perm, P.perm.size() + 32);
+  ALLOC(A.warp_begin, P.warp_begin.size());
+  ALLOC(A.long_rows, P.long_rows.size() + 1);
+  ALLOC(A.partials, (size_t)P.grid * MAX_RED);
+  ALLOC(A.ticket, 1);
+  CU(cudaMemcpyAsync(A.pieces, P.pieces.data(), sizeof(Piece) * P.pieces.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.perm, P.perm.data(), sizeof(int) * P.perm.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(A.warp_begin, P.warp_begin.data(), sizeof(int) * P.warp_begin.size(), cudaMemcpyHostToDevice, st));
+  if (!P.long_rows.empty())
+    CU(cudaMemcpyAsync(A.long_rows, P.long_rows.data(), sizeof(int) * P.long_rows.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(A.ticket, 0, sizeof(unsigned int), st));
+  return repack<T>(E, A);
+}
+
 template <typename T>
 static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nnz, const int32_t* rowptr,
                       const int32_t* colidx, const void* vals) {
@@ -1125,43 +1167,175 @@ static int upload_csr(EngineT<T>* E, DeviceCsr<T>& A, int rows, int cols, int nn
   for (int r = 0; r < rows; ++r)
     if (h_rowptr[r + 1] < h_rowptr[r]) return fail(PDLP_ERR_INVALID, "rowptr is not monotone");
   tr.lap("csr copy + rowptr to host");
-  using Cfg = StreamCfg<T>;
-  HostSell P = build_sell_plan(h_rowptr.data(), rows, (int)sizeof(T), Cfg::W, Cfg::KB, PDLP_SIGMA, PDLP_LONG_ROW, PDLP_WARP_ROW,
-                               E->base->sms * PDLP_CTAS * PDLP_OVERSUB);
+  HostSell P = plan_csr<T>(E, A);
   tr.lap("plan (host)");
-  // ring geometry: a stage holds the largest piece of THIS matrix; as many stages as the budget allows
-  A.stage_bytes = (P.max_piece_bytes + 127) / 128 * 128;
-  A.nstages = std::max(2, std::min(Cfg::SMAX, (int)(PDLP_SMEM_BUDGET / PDLP_CTAS / ((size_t)Cfg::W * A.stage_bytes))));
-  A.smem_bytes = Cfg::W * A.nstages * A.stage_bytes + 128;
-  if (P.packed_bytes / 16 >= 0xffffffffull) return fail(PDLP_ERR_INVALID, "packed matrix exceeds 64 GiB");
-  A.grid = P.grid;
-  A.npieces = (int)P.pieces.size();
-  A.nlong = (int)P.long_rows.size();
-  A.packed_bytes = P.packed_bytes;
-  ALLOC(A.packed, P.packed_bytes + 16);
-  ALLOC(A.pieces, P.pieces.size() + 1);
-  ALLOC(A.perm, P.perm.size() + 32);
-  ALLOC(A.warp_begin, P.warp_begin.size());
-  ALLOC(A.long_rows, P.long_rows.size() + 1);
-  ALLOC(A.partials, (size_t)P.grid * MAX_RED);
-  ALLOC(A.ticket, 1);
-  CU(cudaMemcpyAsync(A.pieces, P.pieces.data(), sizeof(Piece) * P.pieces.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A.perm, P.perm.data(), sizeof(int) * P.perm.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(A.warp_begin, P.warp_begin.data(), sizeof(int) * P.warp_begin.size(), cudaMemcpyHostToDevice, st));
-  if (!P.long_rows.empty())
-    CU(cudaMemcpyAsync(A.long_rows, P.long_rows.data(), sizeof(int) * P.long_rows.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(A.ticket, 0, sizeof(unsigned int), st));
-  int rc = repack<T>(E, A);
+  int rc = upload_plan_and_pack<T>(E, A, P);
   if (rc) return rc;
   CU(cudaStreamSynchronize(st));
   tr.lap("alloc + plan upload + pack");
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// ingest of a HOST CSR matrix (pdlp_create_host): H2D copies, 32-bit indices, canonical-form check, and the CSR of
+// K^T built on the device, overlapped with the host-side planning.  The reference does this with ATen calls spread
+// over PDLP/util.py:239-269 and K.to(device) (primal_dual_hybrid_gradient.py:7 receives the device tensor).
+// ---------------------------------------------------------------------------
+// one thread per entry: 32-bit column, owning row (binary search in rowptr), canonical-form check (columns strictly
+// increasing inside a row, inside [0, ncols)), identity permutation for the sort, histogram of the columns
+template <typename IDX>
+__global__ void ingest_entries_kernel(const int* __restrict__ rowptr, int rows, const IDX* __restrict__ col_in, int nnz,
+                                      int ncols, int* __restrict__ col_out, int* __restrict__ row_out,
+                                      int* __restrict__ idx_out, int* __restrict__ col_count, int* __restrict__ err) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+    const long long cl = (long long)col_in[e];
+    if (cl < 0 || cl >= ncols) {
+      err[0] = 1;
+      col_out[e] = 0;
+      row_out[e] = 0;
+      idx_out[e] = (int)e;
+      continue;
+    }
+    int lo = 0, hi = rows;                 // last row r with rowptr[r] <= e
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (rowptr[mid] <= (int)e) lo = mid; else hi = mid;
+    }
+    if ((int)e > rowptr[lo] && (long long)col_in[e - 1] >= cl) err[1] = 1;
+    col_out[e] = (int)cl;
+    row_out[e] = lo;
+    idx_out[e] = (int)e;
+    atomicAdd(&col_count[(int)cl], 1);
+  }
+}
+
+// entries of K^T in (column of K, row of K) order: perm = entry indices of K stably sorted by column
+template <typename T>
+__global__ void transpose_fill_kernel(const int* __restrict__ perm, const int* __restrict__ row_of, const T* __restrict__ vals,
+                                      int nnz, int* __restrict__ t_colidx, T* __restrict__ t_vals) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+    const int e = perm[p];
+    t_colidx[p] = row_of[e];
+    t_vals[p] = vals[e];
+  }
+}
+
+template <typename T>
+static int ingest_host_csr(EngineT<T>* E, const void* h_rowptr, const void* h_colidx, int index_bytes, const void* h_vals) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  const int m = (int)B->m, n = (int)B->n, nnz = (int)B->nnz;
+  DeviceCsr<T>&K = E->K, &Kt = E->Kt;
+  SetupTrace tr;
+  K.rows = m; K.cols = n; K.nnz = nnz;
+  Kt.rows = n; Kt.cols = m; Kt.nnz = nnz;
+  // row pointers: validated and narrowed on the host (the planner needs them there anyway)
+  K.h_rowptr.resize((size_t)m + 1);
+  for (int r = 0; r <= m; ++r) {
+    const long long v = index_bytes == 8 ? (long long)((const int64_t*)h_rowptr)[r] : (long long)((const int32_t*)h_rowptr)[r];
+    if (v < 0 || v > nnz || (r > 0 && v < K.h_rowptr[(size_t)r - 1])) return fail(PDLP_ERR_INVALID, "rowptr is not monotone inside [0, nnz]");
+    K.h_rowptr[(size_t)r] = (int)v;
+  }
+  if (K.h_rowptr[0] != 0 || K.h_rowptr[(size_t)m] != nnz) return fail(PDLP_ERR_INVALID, "rowptr does not span [0, nnz]");
+  ALLOC(K.rowptr, m + 1); ALLOC(K.colidx, nnz); ALLOC(K.vals, nnz);
+  ALLOC(Kt.rowptr, n + 1); ALLOC(Kt.colidx, nnz); ALLOC(Kt.vals, nnz);
+  // temporaries (returned to the pool at the end, stream-ordered)
+  void* raw_col = nullptr;
+  int *row_of = nullptr, *idx = nullptr, *perm = nullptr, *keys_out = nullptr, *cnt = nullptr, *err = nullptr;
+  void* cub_tmp = nullptr;
+  std::vector<void*> tmps;
+  auto tmp_alloc = [&](void** p, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st);
+    if (e == cudaSuccess) tmps.push_back(*p);
+    return e;
+  };
+  auto tmp_free = [&]() {
+    for (void* p : tmps) cudaFreeAsync(p, st);
+    tmps.clear();
+  };
+#define TMP(ptr, bytes)                                                      \
+  do {                                                                       \
+    cudaError_t e_ = tmp_alloc((void**)&(ptr), (bytes));                     \
+    if (e_ != cudaSuccess) {                                                 \
+      tmp_free();                                                            \
+      return fail(PDLP_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e_)); \
+    }                                                                        \
+  } while (0)
+#define CUT(expr)                                                            \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      tmp_free();                                                            \
+      return fail(PDLP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    }                                                                        \
+  } while (0)
+  TMP(raw_col, (size_t)nnz * (size_t)index_bytes);
+  TMP(row_of, sizeof(int) * (size_t)nnz);
+  TMP(idx, sizeof(int) * (size_t)nnz);
+  TMP(perm, sizeof(int) * (size_t)nnz);
+  TMP(keys_out, sizeof(int) * (size_t)nnz);
+  TMP(cnt, sizeof(int) * ((size_t)n + 1));
+  TMP(err, sizeof(int) * 2);
+  int end_bit = 1;
+  while (end_bit < 31 && (1ll << end_bit) < (long long)n) ++end_bit;
+  size_t scan_bytes = 0, sort_bytes = 0;
+  CUT(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, Kt.rowptr, n + 1, st));
+  CUT(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const int*)K.colidx, keys_out, (const int*)idx, perm, nnz, 0, end_bit, st));
+  TMP(cub_tmp, std::max(scan_bytes, sort_bytes));
+  // H2D: pinned sources are DMA'd asynchronously (the host plans K meanwhile), pageable ones are staged by the driver
+  CUT(cudaMemcpyAsync(K.rowptr, K.h_rowptr.data(), sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, st));
+  CUT(cudaMemcpyAsync(raw_col, h_colidx, (size_t)nnz * (size_t)index_bytes, cudaMemcpyHostToDevice, st));
+  CUT(cudaMemcpyAsync(K.vals, h_vals, sizeof(T) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+  CUT(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), st));
+  CUT(cudaMemsetAsync(err, 0, sizeof(int) * 2, st));
+  if (nnz > 0) {
+    const int blocks = (int)std::min<int64_t>(((int64_t)nnz + 255) / 256, (int64_t)B->sms * 32);
+    if (index_bytes == 8)
+      ingest_entries_kernel<int64_t><<<blocks, 256, 0, st>>>(K.rowptr, m, (const int64_t*)raw_col, nnz, n, K.colidx, row_of, idx, cnt, err);
+    else
+      ingest_entries_kernel<int32_t><<<blocks, 256, 0, st>>>(K.rowptr, m, (const int32_t*)raw_col, nnz, n, K.colidx, row_of, idx, cnt, err);
+    CUT(cudaGetLastError());
+  }
+  CUT(cub::DeviceScan::ExclusiveSum(cub_tmp, scan_bytes, cnt, Kt.rowptr, n + 1, st));
+  if (nnz > 0) {
+    CUT(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, (const int*)K.colidx, keys_out, (const int*)idx, perm, nnz, 0, end_bit, st));
+    const int blocks = (int)std::min<int64_t>(((int64_t)nnz + 255) / 256, (int64_t)B->sms * 32);
+    transpose_fill_kernel<T><<<blocks, 256, 0, st>>>(perm, row_of, K.vals, nnz, Kt.colidx, Kt.vals);
+    CUT(cudaGetLastError());
+  }
+  tr.lap("host csr: copies + kernels issued");
+  // while the device copies and transposes: plan K on the host
+  HostSell PK = plan_csr<T>(E, K);
+  tr.lap("plan K (host, overlapped)");
+  int h_err[2] = {0, 0};
+  Kt.h_rowptr.resize((size_t)n + 1);
+  CUT(cudaMemcpyAsync(Kt.h_rowptr.data(), Kt.rowptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+  CUT(cudaMemcpyAsync(h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
+  CUT(cudaStreamSynchronize(st));
+  tmp_free();
+#undef TMP
+#undef CUT
+  if (h_err[0]) return fail(PDLP_ERR_INVALID, "column index outside [0, n)");
+  if (h_err[1]) return fail(PDLP_ERR_NOT_CANONICAL, "K is not a canonical CSR matrix (columns must be strictly increasing inside every row)");
+  if (Kt.h_rowptr[(size_t)n] != nnz) return fail(PDLP_ERR_STATE, "transpose does not cover the matrix");
+  tr.lap("wait: H2D + transpose");
+  int rc = upload_plan_and_pack<T>(E, K, PK);          // the device packs K while the host plans K^T
+  if (rc) return rc;
+  HostSell PT = plan_csr<T>(E, Kt);
+  tr.lap("plan K^T (host, overlapped)");
+  rc = upload_plan_and_pack<T>(E, Kt, PT);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));                        // PK, PT go out of scope
+  tr.lap("plan uploads + packs");
+  return 0;
+}
+
 template <typename T>
 static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
                          const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
-                         const void* q, const void* l, const void* u) {
+                         const void* q, const void* l, const void* u, int host_index_bytes = 0) {
+  // host_index_bytes != 0: K_rowptr / K_colidx / K_vals are HOST arrays with 4- or 8-byte indices and K^T is built
+  // here (pdlp_create_host); c, q, l, u may then live on either side (cudaMemcpyDefault)
   EngineT<T>* E = new EngineT<T>();
   E->base = B;
   B->impl = E;
@@ -1169,10 +1343,16 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   cudaStream_t st = B->stream;
   SetupTrace tr;
   // per-row epilogue traffic expressed in nonzero-equivalents (12 or 8 bytes per nonzero)
-  int rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals);
-  if (rc) return rc;
-  rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals);
-  if (rc) return rc;
+  int rc;
+  if (host_index_bytes) {
+    rc = ingest_host_csr<T>(E, K_rowptr, K_colidx, host_index_bytes, K_vals);
+    if (rc) return rc;
+  } else {
+    rc = upload_csr<T>(E, E->K, m, n, nnz, K_rowptr, K_colidx, K_vals);
+    if (rc) return rc;
+    rc = upload_csr<T>(E, E->Kt, n, m, nnz, Kt_rowptr, Kt_colidx, Kt_vals);
+    if (rc) return rc;
+  }
   layout_from_env(&E->k1, &E->k2);
   if (E->k2 == 1) {
     rc = build_run<T>(E, E->K);
@@ -1205,7 +1385,7 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   ALLOC(E->y, m + 4);      // the panel kernel's bulk copies round the last panel up to 16 bytes
   ALLOC(E->ysum, m); ALLOC(E->ylast, m); ALLOC(E->Y4, m);
   ALLOC(E->drow, m); ALLOC(E->dcol, n);
-  ALLOC(E->tmp_n, n); ALLOC(E->tmp_n2, n); ALLOC(E->tmp_m, m);
+  ALLOC(E->tmp_n, n); ALLOC(E->tmp_m, m);
   ALLOC(E->kty_old, n); ALLOC(E->lam_prev, n);
   CU(cudaMemsetAsync(E->kty_old, 0, sizeof(T) * n, st));
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
@@ -1223,10 +1403,11 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   ALLOC(E->blk_bar, 4);
   ALLOC(E->ew_ticket, 1);
   CU(cudaMemsetAsync(E->ew_ticket, 0, sizeof(unsigned int), st));
-  CU(cudaMemcpyAsync(E->c, c, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(E->l, l, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(E->u, u, sizeof(T) * n, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(E->q, q, sizeof(T) * m, cudaMemcpyDeviceToDevice, st));
+  const cudaMemcpyKind vkind = host_index_bytes ? cudaMemcpyDefault : cudaMemcpyDeviceToDevice;
+  CU(cudaMemcpyAsync(E->c, c, sizeof(T) * n, vkind, st));
+  CU(cudaMemcpyAsync(E->l, l, sizeof(T) * n, vkind, st));
+  CU(cudaMemcpyAsync(E->u, u, sizeof(T) * n, vkind, st));
+  CU(cudaMemcpyAsync(E->q, q, sizeof(T) * m, vkind, st));
   pack_clu_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(E->c, E->l, E->u, E->clu, n);
   CU(cudaMemsetAsync(E->X4, 0, sizeof(Quad<T>) * n, st));
   CU(cudaMemsetAsync(E->Y4, 0, sizeof(Quad<T>) * m, st));
@@ -1573,22 +1754,21 @@ static int engine_kkt(EngineT<T>* E, const void* x, const void* y, double omega,
 
 template <typename T>
 static int enqueue_power_rounds(EngineT<T>* E, int iters, cudaStream_t st) {
-  pdlp_engine* B = E->base;
-  const int n = (int)B->n;
-  T* b = E->tmp_n;
-  T* v = E->tmp_n2;
+  T* v = E->tmp_n;         // un-normalised iterate; ||v||^2 lives in scratch[2]
   T* w = E->tmp_m;
-  // (folding b = v / ||v|| into the next pass's gather was measured: the fp64 division per gathered element makes
-  // the iteration slower, 110 vs 88 us, so the normalisation stays a separate streaming kernel)
+  // helpers.py:48-50: b = K^T (K b); b /= ||b||.  The division is applied to the ROWS of the next product,
+  // K (v / ||v||) = (K v) / ||v||, so a round is two kernels and v is never rewritten (a separate normalisation pass
+  // cost ~18 of 88 us per round on config 2; dividing every GATHERED element instead made the round slower, 110 us).
+  // A zero iterate (K = 0) divides by zero and yields NaN, like the reference.
   for (int i = 0; i < iters; ++i) {
-    SpmvOp<T, false> f{b, w, E->S, 2};
+    SpmvOp<T, false> f{v, w, E->S, 2};
+    f.div_slot = i > 0 ? 2 : -1;
     CU(launch_stream(E->K, f, st));
     SpmvOp<T, true> g{w, v, E->S, 2};
     CU(launch_stream(E->Kt, g, st));
-    normalize_kernel<T><<<ew_blocks(n, B->sms), 256, 0, st>>>(v, b, n, E->S, 2);
-    CU(cudaGetLastError());
   }
-  SpmvOp<T, true> f{b, w, E->S, 3};
+  SpmvOp<T, true> f{v, w, E->S, 3};
+  f.div_slot = iters > 0 ? 2 : -1;
   CU(launch_stream(E->K, f, st));
   return 0;
 }
@@ -2104,45 +2284,91 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
     if (e_ != cudaSuccess) return fail(PDLP_ERR_CUDA, cudaGetErrorString(e_)); \
   } while (0)
 
-extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
-                           const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
-                           const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
-                           const void* q, const void* l, const void* u, void* stream) {
+static int create_common(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                         const void* K_rowptr, const void* K_colidx, const void* K_vals, const int32_t* Kt_rowptr,
+                         const int32_t* Kt_colidx, const void* Kt_vals, const void* c, const void* q, const void* l,
+                         const void* u, void* stream, int host_index_bytes) {
   if (!out) return fail(PDLP_ERR_INVALID, "out is null");
   *out = nullptr;
   if (dtype != PDLP_F64 && dtype != PDLP_F32) return fail(PDLP_ERR_INVALID, "dtype must be PDLP_F64 or PDLP_F32");
   if (m <= 0 || n <= 0 || m_ineq < 0 || m_ineq > m || nnz < 0) return fail(PDLP_ERR_INVALID, "bad dimensions");
   if (m >= INT32_MAX - 64 || n >= INT32_MAX - 64 || nnz >= INT32_MAX - 64)
     return fail(PDLP_ERR_INVALID, "dimensions exceed int32 indexing");
-  if (!K_rowptr || !Kt_rowptr || !c || !q || !l || !u || (nnz > 0 && (!K_colidx || !K_vals || !Kt_colidx || !Kt_vals)))
+  const bool host = host_index_bytes != 0;
+  if (host && host_index_bytes != 4 && host_index_bytes != 8) return fail(PDLP_ERR_INVALID, "index_bytes must be 4 or 8");
+  if (!K_rowptr || !c || !q || !l || !u || (nnz > 0 && (!K_colidx || !K_vals)))
     return fail(PDLP_ERR_INVALID, "null problem pointer");
-  int dev = 0;
+  if (!host && (!Kt_rowptr || (nnz > 0 && (!Kt_colidx || !Kt_vals)))) return fail(PDLP_ERR_INVALID, "null problem pointer");
+  SetupTrace tr;
+  int dev = 0, cc_major = 0, sms = 0;
   CU(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major < 9) return fail(PDLP_ERR_CUDA, "pdlp_b200 needs TMA bulk copies (built for sm_100a)");
+  // (two attribute queries, not cudaGetDeviceProperties: that call asks the kernel driver for every property of the
+  // device and takes milliseconds -- tens of them when other processes keep the driver busy -- on every engine build)
+  CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major < 9) return fail(PDLP_ERR_CUDA, "pdlp_b200 needs TMA bulk copies (built for sm_100a)");
   pdlp_engine* B = new pdlp_engine();
   B->dtype = dtype; B->device = dev; B->stream = (cudaStream_t)stream;
   B->m = m; B->n = n; B->m_ineq = m_ineq; B->nnz = nnz;
-  B->sms = prop.multiProcessorCount;
+  B->sms = sms;
   init_l2_persistence();
   {
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // keep freed blocks in the device's default pool: the next engine build does not go back to the driver
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (std::find(done.begin(), done.end(), dev) == done.end()) {
+      cudaMemPool_t pool;
+      CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = UINT64_MAX;
+      CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      done.push_back(dev);
+    }
   }
+  tr.lap("create: device queries");
+  const int32_t *kr = (const int32_t*)K_rowptr, *kc = (const int32_t*)K_colidx;   // (host path: reinterpreted by index_bytes)
   int rc = dtype == PDLP_F64
-               ? engine_create<double>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u)
-               : engine_create<float>(B, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u);
+               ? engine_create<double>(B, kr, kc, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u, host_index_bytes)
+               : engine_create<float>(B, kr, kc, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l, u, host_index_bytes);
   if (!rc) rc = dtype == PDLP_F64 ? refresh_norms<double>((EngineT<double>*)B->impl)
                                   : refresh_norms<float>((EngineT<float>*)B->impl);
+  tr.lap("create: engine + norms");
   if (rc) {
+    const std::string msg = g_err;                    // (the teardown must not replace the message)
     if (dtype == PDLP_F64) engine_destroy<double>(B); else engine_destroy<float>(B);
     delete B;
+    g_err = msg;
     return rc;
   }
   *out = B;
+  return 0;
+}
+
+extern "C" int pdlp_create(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                           const int32_t* K_rowptr, const int32_t* K_colidx, const void* K_vals,
+                           const int32_t* Kt_rowptr, const int32_t* Kt_colidx, const void* Kt_vals, const void* c,
+                           const void* q, const void* l, const void* u, void* stream) {
+  return create_common(out, dtype, m, n, m_ineq, nnz, K_rowptr, K_colidx, K_vals, Kt_rowptr, Kt_colidx, Kt_vals, c, q, l,
+                       u, stream, 0);
+}
+
+extern "C" int pdlp_create_host(pdlp_handle* out, int dtype, int64_t m, int64_t n, int64_t m_ineq, int64_t nnz,
+                                const void* host_K_rowptr, const void* host_K_colidx, int32_t index_bytes,
+                                const void* host_K_vals, const void* c, const void* q, const void* l, const void* u,
+                                void* stream) {
+  return create_common(out, dtype, m, n, m_ineq, nnz, host_K_rowptr, host_K_colidx, host_K_vals, nullptr, nullptr, nullptr,
+                       c, q, l, u, stream, index_bytes ? index_bytes : -1);
+}
+
+extern "C" int pdlp_get_matrix_structure(pdlp_handle h, int32_t* K_rowptr, int32_t* K_colidx) {
+  if (!h || !h->impl) return fail(PDLP_ERR_INVALID, "null handle");
+  cudaError_t e_ = cudaSetDevice(h->device);
+  if (e_ != cudaSuccess) return fail(PDLP_ERR_CUDA, cudaGetErrorString(e_));
+  const int* rp; const int* ci;
+  if (h->dtype == PDLP_F64) { auto* E = (EngineT<double>*)h->impl; rp = E->K.rowptr; ci = E->K.colidx; }
+  else { auto* E = (EngineT<float>*)h->impl; rp = E->K.rowptr; ci = E->K.colidx; }
+  if (K_rowptr) CU(cudaMemcpyAsync(K_rowptr, rp, sizeof(int) * ((size_t)h->m + 1), cudaMemcpyDeviceToDevice, h->stream));
+  if (K_colidx) CU(cudaMemcpyAsync(K_colidx, ci, sizeof(int) * (size_t)h->nnz, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
 }
 

@@ -156,13 +156,21 @@ struct SpmvOp {
   T* out;
   Scalars* S;
   int slot;
-  __device__ bool begin() { return true; }
+  // div_slot >= 0: out = (A in) / sqrt(scratch[div_slot]) -- the power iteration's b = v / ||v|| (helpers.py:50)
+  // applied once per ROW of the product instead of once per element of v in a pass of its own
+  int div_slot = -1;
+  T nrm = T(1);
+  __device__ bool begin() {
+    if (div_slot >= 0) nrm = (T)sqrt(S->scratch[div_slot]);
+    return true;
+  }
   __device__ T gather(int col) const { return ldg(in + col); }
   __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
   __device__ Ctx row_load(int) const { return Ctx{}; }
   __device__ void row_finish(int r, const Ctx&, const T (&acc)[1], double (&red)[1]) {
-    out[r] = acc[0];
-    if (SUMSQ) red[0] += (double)acc[0] * (double)acc[0];
+    const T o = div_slot >= 0 ? acc[0] / nrm : acc[0];
+    out[r] = o;
+    if (SUMSQ) red[0] += (double)o * (double)o;
   }
   __device__ void finalize(const double (&tot)[1]) { S->scratch[slot] = tot[0]; }
 };
@@ -1385,14 +1393,6 @@ __global__ void pack3_kernel(const T* x, Quad<T>* X4, int n) {
     const T v = x[j];
     X4[j] = Quad<T>{{v, v, v, T(0)}};
   }
-}
-
-// b = v / sqrt(scratch[slot])   (helpers.py:50)
-template <typename T>
-__global__ void normalize_kernel(const T* v, T* b, int n, const Scalars* S, int slot) {
-  const T nrm = (T)sqrt(S->scratch[slot]);
-  const int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) b[j] = v[j] / nrm;
 }
 
 // c^T x of the current iterate -> scratch[slot] (single block, fixed order)

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
+import time
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -114,6 +116,34 @@ def to_device_csr(K, device: torch.device, dtype: torch.dtype):
     return (m, n, int(vals.numel())), csr, csc
 
 
+def host_csr_arrays(K, dtype: torch.dtype):
+    """(crow, col, vals, (m, n)) as contiguous CPU tensors when ``K`` is a CSR matrix in HOST memory (torch sparse CSR
+    on the CPU, scipy CSR, or a (crow, col, val, shape) tuple of host arrays), else None.  Nothing is converted
+    element-wise here except a value dtype that differs from the engine's: the library takes 4- or 8-byte indices."""
+    if isinstance(K, tuple):
+        crow, col, val, shape = K
+        parts = [torch.as_tensor(a) for a in (crow, col, val)]
+        if any(t.device.type != "cpu" for t in parts):
+            return None
+        crow, col, val = parts
+    elif isinstance(K, torch.Tensor):
+        if K.layout != torch.sparse_csr or K.device.type != "cpu" or K.dim() != 2:
+            return None
+        crow, col, val, shape = K.crow_indices(), K.col_indices(), K.values(), K.shape
+    elif hasattr(K, "indptr") and hasattr(K, "indices") and getattr(K, "format", None) == "csr":   # scipy CSR
+        crow, col, val, shape = torch.from_numpy(K.indptr), torch.from_numpy(K.indices), \
+            torch.from_numpy(np.ascontiguousarray(K.data)), K.shape
+    else:
+        return None
+    if crow.dtype not in (torch.int32, torch.int64):
+        crow = crow.to(torch.int64)
+    if col.dtype != crow.dtype:
+        col = col.to(crow.dtype)
+    if val.dtype != dtype:
+        val = val.to(dtype)
+    return crow.contiguous(), col.contiguous(), val.contiguous(), (int(shape[0]), int(shape[1]))
+
+
 @dataclass
 class SolveOutput:
     x: torch.Tensor
@@ -139,22 +169,57 @@ class Engine:
         if dtype not in (torch.float64, torch.float32):
             raise TypeError("dtype must be float64 or float32")
         self.dtype = dtype
+        trace = os.environ.get("PDLP_TRACE_SETUP")
+        t_trace = [time.perf_counter()]
+
+        def lap(what):
+            if trace:
+                t_trace.append(time.perf_counter())
+                print(f"[pdlp engine] {what:28s} {1e3 * (t_trace[-1] - t_trace[-2]):8.3f} ms", file=sys.stderr)
+
+        self.h = None
+        self._csr = None             # structure of K as torch tensors, fetched lazily for matrix()
+        self.ingest = "device"       # "host": the library copied and transposed a host CSR itself (pdlp_create_host)
         with torch.cuda.device(self.device):
-            (self.m, self.n, self.nnz), csr, csc = to_device_csr(K, self.device, dtype)
             self.m_ineq = int(m_ineq)
-            vec = lambda v, ln: torch.as_tensor(v, dtype=dtype).reshape(-1).to(self.device).contiguous()
-            c, q, l, u = vec(c, self.n), vec(q, self.m), vec(l, self.n), vec(u, self.n)
-            if c.numel() != self.n or l.numel() != self.n or u.numel() != self.n or q.numel() != self.m:
-                raise ValueError("vector sizes do not match K")
-            self._csr = csr          # kept for matrix() / debugging (structure only is reused)
             self.stream = torch.cuda.current_stream(self.device)
-            h = C.c_void_p()
-            torch.cuda.synchronize(self.device)
-            check(self.lib.pdlp_create(C.byref(h), 0 if dtype == torch.float64 else 1, self.m, self.n, self.m_ineq,
-                                       self.nnz, csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
-                                       csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), c.data_ptr(),
-                                       q.data_ptr(), l.data_ptr(), u.data_ptr(), self.stream.cuda_stream))
-            self.h = h
+            dcode = 0 if dtype == torch.float64 else 1
+            host = host_csr_arrays(K, dtype) if os.environ.get("PDLP_HOST_INGEST", "1") != "0" else None
+            if host is not None:
+                crow, col, val, (m, n) = host
+                # the vectors stay where they are (host or this device): the library copies with unified addressing
+                vec = lambda v: self._place(torch.as_tensor(v, dtype=dtype).reshape(-1).contiguous())
+                cc, qq, ll, uu = vec(c), vec(q), vec(l), vec(u)
+                if cc.numel() != n or ll.numel() != n or uu.numel() != n or qq.numel() != m or crow.numel() != m + 1 \
+                        or col.numel() != val.numel():
+                    raise ValueError("vector sizes do not match K")
+                h = C.c_void_p()
+                lap("host arrays")
+                try:
+                    check(self.lib.pdlp_create_host(C.byref(h), dcode, m, n, self.m_ineq, int(val.numel()),
+                                                    crow.data_ptr(), col.data_ptr(), crow.element_size(), val.data_ptr(),
+                                                    cc.data_ptr(), qq.data_ptr(), ll.data_ptr(), uu.data_ptr(),
+                                                    self.stream.cuda_stream))
+                    self.h, self.ingest = h, "host"
+                    self.m, self.n, self.nnz = m, n, int(val.numel())
+                except _lib.PdlpError as err:
+                    if err.code != _lib.ERR_NOT_CANONICAL:      # unsorted / duplicate entries: coalesce below
+                        raise
+            if self.h is None:
+                (self.m, self.n, self.nnz), csr, csc = to_device_csr(K, self.device, dtype)
+                vec = lambda v, ln: torch.as_tensor(v, dtype=dtype).reshape(-1).to(self.device).contiguous()
+                c, q, l, u = vec(c, self.n), vec(q, self.m), vec(l, self.n), vec(u, self.n)
+                if c.numel() != self.n or l.numel() != self.n or u.numel() != self.n or q.numel() != self.m:
+                    raise ValueError("vector sizes do not match K")
+                self._csr = csr          # kept for matrix() / debugging (structure only is reused)
+                h = C.c_void_p()
+                torch.cuda.synchronize(self.device)
+                check(self.lib.pdlp_create(C.byref(h), dcode, self.m, self.n, self.m_ineq,
+                                           self.nnz, csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(),
+                                           csc[0].data_ptr(), csc[1].data_ptr(), csc[2].data_ptr(), c.data_ptr(),
+                                           q.data_ptr(), l.data_ptr(), u.data_ptr(), self.stream.cuda_stream))
+                self.h = h
+        lap("create")
         self.bytes_per_iteration = int(self.lib.pdlp_bytes_per_iteration(self.h))
 
     # -- lifetime ---------------------------------------------------------
@@ -168,6 +233,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def _place(self, t: torch.Tensor) -> torch.Tensor:
+        """A vector the library can read from this device: host memory or this GPU."""
+        return t if t.device.type == "cpu" or t.device == self.device else t.to(self.device)
 
     def set_stream(self, stream: "torch.cuda.Stream"):
         check(self.lib.pdlp_set_stream(self.h, stream.cuda_stream))
@@ -285,6 +354,11 @@ class Engine:
         """Current (possibly scaled) K as a torch sparse CSR tensor on the device."""
         vals = self._new(self.nnz)
         check(self.lib.pdlp_get_matrix_values(self.h, vals.data_ptr()))
+        if self._csr is None:
+            crow = torch.empty(self.m + 1, dtype=torch.int32, device=self.device)
+            col = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            check(self.lib.pdlp_get_matrix_structure(self.h, crow.data_ptr(), col.data_ptr()))
+            self._csr = (crow, col)
         return torch.sparse_csr_tensor(self._csr[0].to(torch.int64), self._csr[1].to(torch.int64), vals,
                                        size=(self.m, self.n))
 

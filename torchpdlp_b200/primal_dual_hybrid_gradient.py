@@ -138,6 +138,7 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
             torch.cuda.synchronize()
             trace_t.append((what, time.time()))
 
+    lap("entry")
     engine = _cache.engine_for(K, m_ineq, c, q, l, u, device)
     lap("engine_for")
     scaled = bool(precondition)
