@@ -209,7 +209,10 @@ def run_engine(args):
     barrier()
     ms = e0.elapsed_time(e1)
     # per-kernel durations, CUDA events on the engine's stream (cannot be placed inside the graph replay)
-    prim_ms, dual_ms = eng.time_kernels(200)
+    iso_prim_ms, iso_dual_ms = eng.time_kernels(200)
+    # ... and as they run in the loop: back-to-back launches chained by programmatic dependent launch, every launch
+    # stamped with %globaltimer when it leaves griddepcontrol.wait and after its finalize (pdlp_time_kernels_in_loop)
+    prim_ms, dual_ms, loop_iter_ms = eng.time_kernels_in_loop(400)
     clocks = sampler.stop()
     iters = RESTART_PERIOD * args.steps
     value = iters / (ms * 1e-3)
@@ -293,9 +296,14 @@ def run_engine(args):
                                     "stream_kernel<DualOp> (K xbar + dual update + step rule)"),
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
-                         "primal": {"launch_ms": prim_ms, "algorithmic_bytes": primal_bytes,
+                         "launch_ms_is": "average span of a launch inside the loop (400 iterations chained by programmatic "
+                                         "dependent launch as in the block graph): %globaltimer when its first CTA leaves "
+                                         "griddepcontrol.wait -> after its last CTA's finalize; isolated launches bracketed "
+                                         "by CUDA events (cold start, no overlap with the neighbour) are under `isolated_ms`",
+                         "loop_ms_per_iteration": loop_iter_ms,
+                         "primal": {"launch_ms": prim_ms, "isolated_ms": iso_prim_ms, "algorithmic_bytes": primal_bytes,
                                     "frac": primal_bytes / (prim_ms * 1e-3) / 1e9 / peak},
-                         "dual": {"launch_ms": dual_ms, "algorithmic_bytes": dual_bytes,
+                         "dual": {"launch_ms": dual_ms, "isolated_ms": iso_dual_ms, "algorithmic_bytes": dual_bytes,
                                   "frac": dual_bytes / (dual_ms * 1e-3) / 1e9 / peak}},
             "cpu_baseline": {"value": cpu_coo, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"8 adaptive PDHG iterations of the oracle port on the same LP, torch sparse COO "

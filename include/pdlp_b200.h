@@ -213,6 +213,14 @@ int pdlp_iterate(pdlp_handle h, int n_iters, int save_previous, int use_graph);
  * the average device time per launch (milliseconds) of the primal (K^T y) and dual (K xbar)
  * kernels.  Advances the solver state like pdlp_iterate.  Synchronises. */
 int pdlp_time_kernels(pdlp_handle h, int n_iters, float* host_primal_ms, float* host_dual_ms);
+/* The same two kernels timed as they run in the loop: n_iters iterations launched back to back with programmatic
+ * dependent launch (nothing between the kernels, so the overlap of a kernel's prologue with its predecessor's tail
+ * and the warm L2 are those of the block graph); every launch records %globaltimer when its first CTA leaves
+ * griddepcontrol.wait and after its last CTA's finalize.  Returns the average of those spans per kernel and the
+ * event-timed wall time per iteration (milliseconds).  Default layout (SELL, single pass, no infeasibility
+ * detection) only: PDLP_ERR_STATE otherwise.  Advances the solver state.  Synchronises. */
+int pdlp_time_kernels_in_loop(pdlp_handle h, int n_iters, float* host_primal_ms, float* host_dual_ms,
+                              float* host_iteration_ms);
 
 /* Restart test + restart epilogue (:115-177): averages, the three KKT errors
  * with ONE pass over K and one over K^T, the sufficient / necessary / artificial

@@ -449,3 +449,23 @@ def test_host_ingest_rejects_and_falls_back(cfg1):
     with pytest.raises(_lib.PdlpError, match="outside"):
         Engine((torch.from_numpy(K.indptr.astype(np.int64)), torch.from_numpy(bad), torch.from_numpy(K.data), K.shape), *args)
     ref.close()
+
+
+def test_in_loop_kernel_timing(cfg1):
+    """pdlp_time_kernels_in_loop: every launch leaves its stamps, the two spans are positive and fit inside the
+    event-timed iteration, and the call advances the solver like pdlp_iterate (bitwise the same iterate)."""
+    a, b = make_engine(cfg1), make_engine(cfg1)
+    for e in (a, b):
+        e.set_iterate(None, None)
+        e.set_step(0.05, 1.0, 1.0, adaptive=True)
+    p_ms, d_ms, it_ms = a.time_kernels_in_loop(60)
+    b.iterate(60, use_graph=True)
+    assert 0 < p_ms < it_ms and 0 < d_ms < it_ms and p_ms + d_ms <= 1.05 * it_ms
+    assert a.state().k == b.state().k == 60
+    for u, v in zip(a.get_iterate(), b.get_iterate()):
+        assert torch.equal(u, v)
+    a.set_options(1e-4, False, True, 1e-4)          # infeasibility detection adds a third kernel: not covered
+    with pytest.raises(Exception, match="default"):
+        a.time_kernels_in_loop(4)
+    a.close()
+    b.close()

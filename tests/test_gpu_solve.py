@@ -466,3 +466,50 @@ def test_engine_cache_never_serves_a_stale_problem(cfg1):
     b = pdlp_algorithm(K, m_ineq, c, q, l, u, "cuda", verbose=False, adaptive=True)[1]
     assert rel(a, b) > 1e-4
     _cache.clear()
+
+
+def _solve_record(lp, monkeypatch, pipelined, **kw):
+    if pipelined:
+        monkeypatch.delenv("PDLP_NO_PIPELINE", raising=False)
+    else:
+        monkeypatch.setenv("PDLP_NO_PIPELINE", "1")
+    x, obj, k, n, j, status, _, info = solve(lp, **kw)
+    trace = [(c.kind, c.use_average, c.t, c.solved, c.k, c.omega, c.kkt_current, c.kkt_average, c.point.prim_obj,
+              c.point.adj_dual) for c in info["trace"]]
+    return x.cpu(), info["y"].cpu(), obj, k, n, j, status, trace
+
+
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_pipelined_solve_is_bitwise_the_sequential_solve(adaptive, pw, cfg1, monkeypatch):
+    """pdlp_solve issues the next block and restart test before it reads the previous test's record (the restart is
+    applied on the device; a solved restart point raises `stop` so the work issued ahead runs as no-ops).  Same
+    iterate, counters, status and per-restart records as the sequential loop, bit for bit -- to convergence and at
+    KKT-pass limits on either side of every place where the budget ends the pipelining."""
+    kw = dict(adaptive=adaptive, primal_weight=pw)
+    a = _solve_record(cfg1, monkeypatch, True, **kw)
+    b = _solve_record(cfg1, monkeypatch, False, **kw)
+    assert a[6] == "Solved" and a[2:8] == b[2:8]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # the engine is not left stopped: a further block moves the iterate
+    from torchpdlp_b200.engine import Engine
+    from torchpdlp_b200.primal_dual_hybrid_gradient import initial_step
+    monkeypatch.delenv("PDLP_NO_PIPELINE", raising=False)
+    eng = Engine(cfg1.K, cfg1.m_ineq, cfg1.c, cfg1.q, cfg1.l, cfg1.u)
+    torch.manual_seed(0)
+    eta, omega, _ = initial_step(eng, 100)
+    eng.set_iterate(None, None)
+    eng.set_counters(0, 0)
+    eng.set_step(eta, omega, 1.0, adaptive)
+    eng.set_options(1e-4, pw, False, 1e-4)
+    out = eng.solve()
+    assert (out.status, out.k, out.n, out.j) == (a[6], a[3], a[4], a[5]) and torch.equal(out.x.cpu().reshape(-1), a[0].reshape(-1))
+    x0, _ = eng.get_iterate()
+    eng.iterate(40, save_previous=True)
+    x1, _ = eng.get_iterate()
+    assert not torch.equal(x0, x1) and eng.state().k == out.k + 40
+    eng.close()
+    for limit in (1, 39, 40, 44, 45, 46, 84, 85, 86, 88, 89, 90, 91, 95, 130, 131, 135, 136, 137, 200, 333):
+        a = _solve_record(cfg1, monkeypatch, True, max_kkt=limit, **kw)
+        b = _solve_record(cfg1, monkeypatch, False, max_kkt=limit, **kw)
+        assert a[2:8] == b[2:8], (limit, a[2:7], b[2:7])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), limit

@@ -84,6 +84,7 @@ SYMBOLS = {
     "pdlp_set_counters": (_I, [_P, _L, C.c_int32]),
     "pdlp_iterate": (_I, [_P, _I, _I, _I]),
     "pdlp_time_kernels": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "pdlp_time_kernels_in_loop": (_I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pdlp_restart_check": (_I, [_P, _I, C.POINTER(Check)]),
     "pdlp_kkt": (_I, [_P, _P, _P, _D, C.POINTER(Residuals)]),
     "pdlp_primal_objective": (_I, [_P, C.POINTER(_D)]),

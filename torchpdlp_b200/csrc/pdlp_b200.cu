@@ -670,6 +670,11 @@ struct EngineT {
   cudaGraphExec_t check_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [force][have_prev]
   bool check_warm[2][2] = {{false, false}, {false, false}};
   Scalars* h_scalars = nullptr;          // pinned read-back buffer
+  // pipelined solve: the steady-state restart test (force = 0, have_prev = 1) without its read-back, the records of two
+  // tests in flight, and the events that mark their arrival
+  cudaGraphExec_t check_graph_async = nullptr;
+  Scalars* h_rec[2] = {nullptr, nullptr};
+  cudaEvent_t rec_ev[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   // layouts of the two iteration kernels.  k1 (K^T y): 0 = SELL (stream_spmv.cuh), 1 = run layout (run_spmv.cuh),
   // 2 = shared-memory panels (panel_spmv.cuh; falls back to 0 when y does not fit).  k2 (K x): 0 = SELL, 1 = run.
@@ -757,7 +762,8 @@ static cudaError_t ensure_smem_attr(F* func, int bytes) {
 
 template <class Op>
 static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op op, cudaStream_t st,
-                                 const void* gathered = nullptr, size_t gathered_bytes = 0) {
+                                 const void* gathered = nullptr, size_t gathered_bytes = 0,
+                                 unsigned long long* stamp = nullptr) {
   using T = typename Op::value_type;
   {
     cudaError_t e = ensure_smem_attr(stream_kernel<Op>, StreamCfg<T>::MAX_SMEM_BYTES - 4096);
@@ -782,7 +788,9 @@ static cudaError_t launch_stream(const DeviceCsr<typename Op::value_type>& A, Op
     attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cfg.numAttrs = 2;
   }
-  return cudaLaunchKernelEx(&cfg, stream_kernel<Op>, A.view(), op);
+  SellView<T> v = A.view();
+  v.stamp = stamp;
+  return cudaLaunchKernelEx(&cfg, stream_kernel<Op>, v, op);
 }
 
 static inline int ew_blocks(int64_t len, int sms) {
@@ -1434,7 +1442,12 @@ static void engine_destroy(pdlp_engine* B) {
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b)
       if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
+  if (E->check_graph_async) cudaGraphExecDestroy(E->check_graph_async);
   if (E->h_scalars) pinned_scalars_put(E->h_scalars);
+  for (int i = 0; i < 2; ++i) {
+    if (E->h_rec[i]) pinned_scalars_put(E->h_rec[i]);
+    if (E->rec_ev[i]) cudaEventDestroy(E->rec_ev[i]);
+  }
   xchg_release(B);
   for (void* p : E->allocs) cudaFreeAsync(p, B->stream);
   cudaStreamSynchronize(B->stream);
@@ -1519,36 +1532,14 @@ static cudaError_t prep_kernel() {
   return ensure_smem_attr(stream_kernel<Op>, StreamCfg<typename Op::value_type>::MAX_SMEM_BYTES - 4096);
 }
 
+// the CUDA graph of a block of n_iters iterations (cached per engine; host work only: nothing is launched)
 template <typename T>
-static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_graph) {
+static int get_block_graph(EngineT<T>* E, int n_iters, int save_prev, cudaGraphExec_t* out) {
   pdlp_engine* B = E->base;
-  cudaStream_t st = B->stream;
-  if (n_iters <= 0) return 0;
-  if (save_prev) B->have_prev = true;
-  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0 && !E->win.on) {
-    // one persistent cooperative kernel for the whole block (SELL layout only; otherwise the CUDA graph below)
-    const int grid = std::max(E->K.grid, E->Kt.grid);
-    const int stages = std::min(E->K.nstages, E->Kt.nstages);
-    const int stage_bytes = std::max(E->K.stage_bytes, E->Kt.stage_bytes);
-    const int smem = StreamCfg<T>::W * stages * stage_bytes + 128;
-    CU(ensure_smem_attr(block_kernel<T>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
-    CU(cudaMemsetAsync(E->blk_bar, 0, sizeof(unsigned int), st));
-    SellView<T> vKt = E->Kt.view(), vK = E->K.view();
-    BlockArgs<T> a{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->q, E->ysum, E->Y4, E->kty_old, E->S,
-                   E->blk_partP, E->blk_partD, E->blk_bar, n_iters, save_prev ? 1 : 0, stages, stage_bytes};
-    void* args[] = {(void*)&vKt, (void*)&vK, (void*)&a};
-    CU(cudaLaunchCooperativeKernel((const void*)block_kernel<T>, dim3(grid), dim3(StreamCfg<T>::NT), args, (size_t)smem, st));
-    return 0;
-  }
-  if (!use_graph || n_iters < 2) {
-    CU(enqueue_iterations<T>(E, n_iters, save_prev, st));
-    return 0;
-  }
-  // (mode 2 with infeasibility detection lands here: CUDA graph)
   const int inf = B->infeas ? 1 : 0;
   for (auto& g : E->graphs)
     if (g.n_iters == n_iters && g.save_prev == (save_prev ? 1 : 0) && g.infeas == inf) {
-      CU(cudaGraphLaunch(g.exec, st));
+      *out = g.exec;
       return 0;
     }
   // first use: set the kernels' attributes outside capture, then capture the whole block
@@ -1596,6 +1587,39 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   cudaGraphDestroy(graph);
   cudaStreamDestroy(cap);
   E->graphs.push_back({n_iters, save_prev ? 1 : 0, inf, exec});
+  *out = exec;
+  return 0;
+}
+
+template <typename T>
+static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_graph) {
+  pdlp_engine* B = E->base;
+  cudaStream_t st = B->stream;
+  if (n_iters <= 0) return 0;
+  if (save_prev) B->have_prev = true;
+  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0 && !E->win.on) {
+    // one persistent cooperative kernel for the whole block (SELL layout only; otherwise the CUDA graph below)
+    const int grid = std::max(E->K.grid, E->Kt.grid);
+    const int stages = std::min(E->K.nstages, E->Kt.nstages);
+    const int stage_bytes = std::max(E->K.stage_bytes, E->Kt.stage_bytes);
+    const int smem = StreamCfg<T>::W * stages * stage_bytes + 128;
+    CU(ensure_smem_attr(block_kernel<T>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
+    CU(cudaMemsetAsync(E->blk_bar, 0, sizeof(unsigned int), st));
+    SellView<T> vKt = E->Kt.view(), vK = E->K.view();
+    BlockArgs<T> a{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->q, E->ysum, E->Y4, E->kty_old, E->S,
+                   E->blk_partP, E->blk_partD, E->blk_bar, n_iters, save_prev ? 1 : 0, stages, stage_bytes};
+    void* args[] = {(void*)&vKt, (void*)&vK, (void*)&a};
+    CU(cudaLaunchCooperativeKernel((const void*)block_kernel<T>, dim3(grid), dim3(StreamCfg<T>::NT), args, (size_t)smem, st));
+    return 0;
+  }
+  if (!use_graph || n_iters < 2) {
+    CU(enqueue_iterations<T>(E, n_iters, save_prev, st));
+    return 0;
+  }
+  // (mode 2 with infeasibility detection lands here: CUDA graph)
+  cudaGraphExec_t exec = nullptr;
+  int rc = get_block_graph<T>(E, n_iters, save_prev, &exec);
+  if (rc) return rc;
   CU(cudaGraphLaunch(exec, st));
   return 0;
 }
@@ -1628,6 +1652,55 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
   for (auto& e : ev) cudaEventDestroy(e);
   *primal_ms = (float)(tp / n_iters);
   *dual_ms = (float)(td / n_iters);
+  return 0;
+}
+
+// The two iteration kernels timed AS THEY RUN IN THE LOOP: n_iters iterations launched back to back with programmatic
+// dependent launch (no events between the kernels, so the overlap of a kernel's prologue with its predecessor's tail
+// and the warm L2 are what the CUDA graph of a block sees), every launch writing its own {start, end} %globaltimer
+// stamps: start when CTA 0 leaves griddepcontrol.wait, end after the last CTA's finalize.  SELL layout, single pass
+// only.  (pdlp_time_kernels brackets every launch with events: isolated launches, cold start, no overlap.)
+template <typename T>
+static int engine_time_kernels_in_loop(EngineT<T>* E, int n_iters, float* primal_ms, float* dual_ms, float* iter_ms) {
+  cudaStream_t st = E->base->stream;
+  if (E->k1 != 0 || E->k2 != 0 || E->win.on || E->base->infeas)
+    return fail(PDLP_ERR_STATE, "in-loop kernel timing covers the default (SELL, single pass) kernels only");
+  if (n_iters < 1) return fail(PDLP_ERR_INVALID, "n_iters must be positive");
+  unsigned long long* d = nullptr;
+  CU(cudaMallocAsync((void**)&d, sizeof(unsigned long long) * 4 * (size_t)n_iters, st));
+  CU(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 4 * (size_t)n_iters, st));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  cudaError_t err = cudaEventRecord(e0, st);
+  for (int i = 0; i < n_iters && err == cudaSuccess; ++i) {
+    PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
+    p.clu = E->clu;
+    err = launch_stream(E->Kt, p, st, nullptr, 0, d + 4 * (size_t)i);
+    if (err != cudaSuccess) break;
+    DualOp<T, false, false> q{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    err = launch_stream(E->K, q, st, nullptr, 0, d + 4 * (size_t)i + 2);
+  }
+  if (err == cudaSuccess) err = cudaEventRecord(e1, st);
+  std::vector<unsigned long long> h(4 * (size_t)n_iters);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(h.data(), d, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFreeAsync(d, st);
+  if (err != cudaSuccess) return fail(PDLP_ERR_CUDA, std::string("in-loop timing: ") + cudaGetErrorString(err));
+  double tp = 0.0, td = 0.0;
+  for (int i = 0; i < n_iters; ++i) {
+    if (!h[4 * (size_t)i] || !h[4 * (size_t)i + 1] || !h[4 * (size_t)i + 2] || !h[4 * (size_t)i + 3])
+      return fail(PDLP_ERR_STATE, "in-loop timing: a launch left no stamp (solver stopped?)");
+    tp += (double)(h[4 * (size_t)i + 1] - h[4 * (size_t)i]);
+    td += (double)(h[4 * (size_t)i + 3] - h[4 * (size_t)i + 2]);
+  }
+  *primal_ms = (float)(tp / n_iters * 1e-6);
+  *dual_ms = (float)(td / n_iters * 1e-6);
+  *iter_ms = ms / (float)n_iters;
   return 0;
 }
 
@@ -1668,10 +1741,12 @@ static void drop_check_graphs(EngineT<T>* E) {
       E->check_graph[a][b] = nullptr;
       E->check_warm[a][b] = false;
     }
+  if (E->check_graph_async) cudaGraphExecDestroy(E->check_graph_async);
+  E->check_graph_async = nullptr;
 }
 
 template <typename T>
-static int enqueue_check(EngineT<T>* E, int force, int have_prev, cudaStream_t st) {
+static int enqueue_check(EngineT<T>* E, int force, int have_prev, cudaStream_t st, bool read_back = true) {
   pdlp_engine* B = E->base;
   const int n = (int)B->n, m = (int)B->m;
   flush_kernel<T><<<ew_blocks(std::max(n, m), B->sms), 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, n, m,
@@ -1684,7 +1759,30 @@ static int enqueue_check(EngineT<T>* E, int force, int have_prev, cudaStream_t s
                                                       n, m, E->S, E->ew_partials, E->ew_ticket);
   post_restart_kernel<<<1, 1, 0, st>>>(E->S, B->scaled ? 1 : 0);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(E->h_scalars, E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+  if (read_back) CU(cudaMemcpyAsync(E->h_scalars, E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// the kernels of a restart test captured into a graph (their attributes are set first: not capturable)
+template <typename T>
+static int capture_check_graph(EngineT<T>* E, int force, int have_prev, bool read_back, cudaGraphExec_t* out) {
+  CU((prep_kernel<KktColsOp<T>>()));
+  CU((prep_kernel<KktRowsOp<T>>()));
+  cudaStream_t cap;
+  CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaError_t e1 = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  int rc = e1 == cudaSuccess ? enqueue_check<T>(E, force, have_prev, cap, read_back) : 0;
+  cudaError_t e2 = e1 == cudaSuccess ? cudaStreamEndCapture(cap, &graph) : e1;
+  if (rc || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    return rc ? rc : fail(PDLP_ERR_CUDA, std::string("check capture failed: ") + cudaGetErrorString(e2));
+  }
+  cudaError_t e3 = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  cudaStreamDestroy(cap);
+  if (e3 != cudaSuccess) return fail(PDLP_ERR_CUDA, std::string("check graph: ") + cudaGetErrorString(e3));
   return 0;
 }
 
@@ -1701,20 +1799,8 @@ static int engine_restart_check(EngineT<T>* E, int force, pdlp_check* out) {
   if (!E->check_graph[f][have_prev]) {
     // first use: run eagerly once (sets kernel attributes), capture for the following calls
     if (E->check_warm[f][have_prev]) {
-      cudaStream_t cap;
-      CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-      cudaGraph_t graph = nullptr;
-      CU(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_check<T>(E, force, have_prev, cap);
-      cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
-      if (rc || e2 != cudaSuccess) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaStreamDestroy(cap);
-        return rc ? rc : fail(PDLP_ERR_CUDA, std::string("check capture failed: ") + cudaGetErrorString(e2));
-      }
-      CU(cudaGraphInstantiate(&E->check_graph[f][have_prev], graph, 0));
-      cudaGraphDestroy(graph);
-      cudaStreamDestroy(cap);
+      int rc = capture_check_graph<T>(E, force, have_prev, true, &E->check_graph[f][have_prev]);
+      if (rc) return rc;
     } else {
       E->check_warm[f][have_prev] = true;
       int rc = enqueue_check<T>(E, force, have_prev, st);
@@ -1773,6 +1859,27 @@ static int enqueue_power_rounds(EngineT<T>* E, int iters, cudaStream_t st) {
   return 0;
 }
 
+// The graphs a solve with the default restart period replays -- the block of 40 iterations and the steady-state
+// restart test -- built ahead of time.  Capture and instantiation are host work only (about a millisecond); called
+// while the GPU runs the power iteration, they leave the critical path of pdlp_algorithm.  Best effort: a failure
+// here is not an error, the solve builds what it misses.
+#ifndef PDLP_DEFAULT_PERIOD
+#define PDLP_DEFAULT_PERIOD 40
+#endif
+template <typename T>
+static void prebuild_graphs(EngineT<T>* E) {
+  pdlp_engine* B = E->base;
+  if (B->infeas || getenv("PDLP_NO_PREBUILD")) return;
+  const std::string keep = g_err;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = get_block_graph<T>(E, PDLP_DEFAULT_PERIOD, 1, &exec) == 0;
+  if (ok && !E->check_graph_async) ok = capture_check_graph<T>(E, 0, 1, false, &E->check_graph_async) == 0;
+  if (!ok) {
+    cudaGetLastError();
+    g_err = keep;
+  }
+}
+
 template <typename T>
 static int engine_power_iteration(EngineT<T>* E, const void* b0, int iters, double* sigma) {
   pdlp_engine* B = E->base;
@@ -1785,6 +1892,7 @@ static int engine_power_iteration(EngineT<T>* E, const void* b0, int iters, doub
     const int rc = enqueue_power_rounds<T>(E, iters, st);
     if (rc) return rc;
   }
+  if (iters >= 10) prebuild_graphs<T>(E);       // the GPU is busy for milliseconds: use the host meanwhile
   double ss;
   CU(cudaMemcpyAsync(&ss, (char*)E->S + offsetof(Scalars, scratch) + 3 * sizeof(double), sizeof(double),
                      cudaMemcpyDeviceToHost, st));
@@ -2199,11 +2307,42 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
   const bool infeas = h.infeas_detect != 0;
   double prim_obj = NAN;
   bool timed_out = false, detected = false;
+  // Pipelined loop (graph mode, no infeasibility detection).  In the steady state every unit of work is the same pair
+  // of graphs -- a block of `period` iterations that saves the previous iterate, then the restart test -- whatever the
+  // test decides: the restart itself is applied on the device.  So the host issues unit i + 1 BEFORE it reads the
+  // record of unit i: the GPU never waits for the host round trip (read-back, wake-up, next launch).  A restart point
+  // that meets the termination test raises Scalars::stop on the device (stop_on_solved), which turns the unit issued
+  // ahead into no-ops; the records of two tests in flight land in two pinned buffers.  A unit is issued ahead only when
+  // the KKT-pass budget covers it in the worst case (this test restarts), so the end game runs the sequential code.
+  const bool pipelined = !infeas && o->use_graph == 1 && !getenv("PDLP_NO_PIPELINE");
+  if (pipelined) {
+    for (int i = 0; i < 2; ++i) {
+      if (!E->h_rec[i]) E->h_rec[i] = (Scalars*)pinned_scalars_get();
+      if (!E->h_rec[i]) return fail(PDLP_ERR_CUDA, "cudaMallocHost failed");
+      if (!E->rec_ev[i]) CU(cudaEventCreateWithFlags(&E->rec_ev[i], cudaEventDisableTiming));
+    }
+    if (!E->check_graph_async) {
+      int rc = capture_check_graph<T>(E, 0, 1, false, &E->check_graph_async);
+      if (rc) return rc;
+    }
+    const int one = 1;
+    CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop_on_solved), &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  // restart test of a steady-state unit, asynchronous: its record lands in h_rec[slot], rec_ev[slot] marks the arrival
+  auto issue_check = [&](int slot) -> int {
+    CU(cudaGraphLaunch(E->check_graph_async, st));
+    CU(cudaMemcpyAsync(E->h_rec[slot], E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(E->rec_ev[slot], st));
+    B->have_prev = false;
+    return 0;
+  };
+  int slot = 0;
+  bool in_flight = false;           // the next unit (block + test) is already issued; its record goes to h_rec[slot]
   while (j < o->max_kkt && status == 1) {
     int t = 0;
     bool restarted = false;
     while (j < o->max_kkt) {
-      if (elapsed() >= o->time_limit) { timed_out = true; break; }
+      if (!in_flight && elapsed() >= o->time_limit) { timed_out = true; break; }
       // iterations until the next restart test, limited by the KKT-pass budget (:67: guard before every iteration)
       int want = period - (t % period);
       int iters = 0;
@@ -2214,8 +2353,14 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
         ++iters;
       }
       const int at_check = ((t + iters) % period == 0) ? 1 : 0;
-      int rc = engine_iterate<T>(E, iters, at_check, o->use_graph);
-      if (rc) return rc;
+      const bool steady = pipelined && iters == period && at_check;
+      int rc = 0;
+      if (!in_flight) {
+        rc = engine_iterate<T>(E, iters, at_check, o->use_graph);
+        if (rc) return rc;
+      } else if (!steady) {
+        return fail(PDLP_ERR_STATE, "pipelined solve: a unit was issued ahead of a non-steady step");
+      }
       if (infeas) {
         // :89-101: the device raised `stop` at the iteration where a certificate test passed
         Scalars hs;
@@ -2233,8 +2378,29 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
       j = jj; k = kk; t += iters;
       if (at_check) {
         pdlp_check chk;
-        rc = engine_restart_check<T>(E, 0, &chk);
-        if (rc) return rc;
+        if (steady) {
+          if (!in_flight) {
+            rc = issue_check(slot);
+            if (rc) return rc;
+          }
+          in_flight = false;
+          // the next unit, ahead of this test's record (worst case for the budget: this test restarts, +3 +2)
+          const bool ahead = j + 5 + period <= o->max_kkt && elapsed() < o->time_limit;
+          if (ahead) {
+            rc = engine_iterate<T>(E, period, 1, o->use_graph);
+            if (!rc) rc = issue_check(slot ^ 1);
+            if (rc) return rc;
+          }
+          CU(cudaEventSynchronize(E->rec_ev[slot]));
+          fill_check(&chk, *E->h_rec[slot]);
+          if (ahead) {
+            in_flight = true;
+            slot ^= 1;
+          }
+        } else {
+          rc = engine_restart_check<T>(E, 0, &chk);
+          if (rc) return rc;
+        }
         j += 3;                                    // :128
         if (chk.kind != PDLP_RESTART_NONE) {
           restarted = true;
@@ -2260,6 +2426,13 @@ static int engine_solve(EngineT<T>* E, const pdlp_solve_options* o, pdlp_solve_r
       if (trace && n_trace < o->max_trace) trace[n_trace++] = chk;
       if (chk.solved) status = 0;
     }
+  }
+  if (pipelined) {
+    // disarm; a unit issued ahead of the final record has run as no-ops behind `stop`, which is lowered again
+    const int zero2[2] = {0, 0};
+    CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop_on_solved), zero2, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (status == 0)
+      CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop), zero2, sizeof(int), cudaMemcpyHostToDevice, st));
   }
   CU(cudaEventRecord(ev1, st));
   CU(cudaEventSynchronize(ev1));
@@ -2662,6 +2835,7 @@ static int t_set_iterate(EngineT<T>* E, const void* x, const void* y) {
   const int zi = 0;
   CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, t), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
   CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
+  CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, stop_on_solved), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
   CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, infeas), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
   CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, infeas_k), &zi, sizeof(int), cudaMemcpyHostToDevice, B->stream));
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * (size_t)n, B->stream));   // pdlp :39-40
@@ -2767,6 +2941,13 @@ extern "C" int pdlp_time_kernels(pdlp_handle h, int n_iters, float* host_primal_
   CHECK_HANDLE(h);
   if (n_iters <= 0 || !host_primal_ms || !host_dual_ms) return fail(PDLP_ERR_INVALID, "bad argument");
   return DISPATCH(h, engine_time_kernels, n_iters, host_primal_ms, host_dual_ms);
+}
+
+extern "C" int pdlp_time_kernels_in_loop(pdlp_handle h, int n_iters, float* host_primal_ms, float* host_dual_ms,
+                                         float* host_iteration_ms) {
+  CHECK_HANDLE(h);
+  if (!host_primal_ms || !host_dual_ms || !host_iteration_ms) return fail(PDLP_ERR_INVALID, "null output");
+  return DISPATCH(h, engine_time_kernels_in_loop, n_iters, host_primal_ms, host_dual_ms, host_iteration_ms);
 }
 
 extern "C" int pdlp_restart_check(pdlp_handle h, int force, pdlp_check* host_out) {

@@ -63,7 +63,10 @@ struct Scalars {
   double batch[24];
   // peer-memory exchange of the row-partitioned engine: sequence number of the next exchange, sticky error
   unsigned long long xchg_seq;
-  int xchg_error, xchg_pad;
+  int xchg_error;
+  // pipelined solve (pdlp_solve): a restart point that meets the termination test raises `stop`, so the block and
+  // the restart test the host issued ahead of reading this test's record run as no-ops
+  int stop_on_solved;
 };
 
 template <typename T>
@@ -1198,6 +1201,7 @@ __host__ __device__ inline Resid make_resid(const double (&s)[S_NSUM], double om
 // restart criteria, primal_dual_hybrid_gradient.py:121-141
 __global__ void decide_kernel(Scalars* S, int force) {
   Scalars& s = *S;
+  if (s.stop) return;
   const Resid rc = make_resid(s.sums[IT_CUR], s.omega);
   const Resid ra = make_resid(s.sums[IT_AVG], s.omega);
   const Resid rp = make_resid(s.sums[IT_PREV], s.omega);
@@ -1230,7 +1234,7 @@ __global__ void decide_kernel(Scalars* S, int force) {
 // after apply_restart: primal weight (enhancements.py:73-78), KKT_first (:153), termination (:173)
 __global__ void post_restart_kernel(Scalars* S, int scaled) {
   Scalars& s = *S;
-  if (s.chk_kind == 0) return;
+  if (s.stop || s.chk_kind == 0) return;
   s.n_restarts += 1;
   if (s.primal_update) {
     const double dxn = sqrt(s.restart_dx2), dyn = sqrt(s.restart_dy2);
@@ -1248,6 +1252,7 @@ __global__ void post_restart_kernel(Scalars* S, int scaled) {
                   p.gap <= s.tol * (1.0 + fabs(p.prim_obj) + fabs(p.adj_dual));     // helpers.py:125-128
   s.chk_solved = ok ? 1 : 0;
   s.solved = ok ? 1 : 0;
+  if (ok && s.stop_on_solved) s.stop = 1;
   s.t = 0;
   s.eta_sum = 0.0;
   s.w_pending = 0.0;
@@ -1260,6 +1265,7 @@ __global__ void post_restart_kernel(Scalars* S, int scaled) {
 template <typename T>
 __global__ void flush_kernel(const Pair<T>* xp, const T* y, T* xsum, T* ysum, Quad<T>* X4, Quad<T>* Y4, int n, int m,
                              const Scalars* S, int have_prev) {
+  if (S->stop) return;
   const T wp = (T)S->w_pending;
   const T es = (T)S->eta_sum;
   const int stride = gridDim.x * blockDim.x;
@@ -1292,7 +1298,7 @@ template <typename T>
 __global__ void apply_restart_kernel(Pair<T>* xp, T* y, T* xsum, T* ysum, const Quad<T>* X4, const Quad<T>* Y4,
                                      T* xlast, T* ylast, int n, int m, Scalars* S, double* partials,
                                      unsigned int* ticket) {
-  if (S->chk_kind == 0) return;
+  if (S->stop || S->chk_kind == 0) return;
   const int slot = S->chk_use_avg ? IT_AVG : IT_CUR;
   const int stride = gridDim.x * blockDim.x;
   double dx2 = 0.0, dy2 = 0.0;

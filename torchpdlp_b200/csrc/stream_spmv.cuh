@@ -87,6 +87,9 @@ struct SellView {
   int stage_bytes;               // ring stage size: the largest piece of this matrix, rounded up to 128
   int nstages;                   // ring stages per warp (2 .. SMAX)
   int grid;                      // CTAs the plan was built for (warp_piece_begin has grid * W + 1 entries)
+  // pdlp_time_kernels_in_loop: {start, end} of this launch in %globaltimer nanoseconds -- start when CTA 0 leaves
+  // griddepcontrol.wait (the previous kernel has completed), end after the last CTA's finalize; null otherwise
+  unsigned long long* stamp = nullptr;
 };
 
 template <typename T>
@@ -491,6 +494,11 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   // tail of the previous kernel in the stream / graph.  From here on we read what that kernel wrote.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (A.stamp && blockIdx.x == 0 && tid == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    A.stamp[0] = now;
+  }
   if (!op.begin()) {
     // drain the copies already in flight before the CTA may retire
     for (int s = 0; s < R.S && pb + s < pe; ++s) mbar_wait(&R.bars[s], 0);
@@ -515,6 +523,11 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
       if (lane == 0) {
         op.finalize(tot);
         *A.ticket = 0u;
+        if (A.stamp) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          A.stamp[1] = now;
+        }
       }
     }
   }

@@ -293,6 +293,13 @@ class Engine:
         check(self.lib.pdlp_time_kernels(self.h, int(n_iters), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def time_kernels_in_loop(self, n_iters: int):
+        """(primal, dual, whole iteration) milliseconds with the kernels chained as in the block graph: each launch's
+        span from leaving griddepcontrol.wait to its finalize (%globaltimer), and the event-timed wall per iteration."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        check(self.lib.pdlp_time_kernels_in_loop(self.h, int(n_iters), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def restart_check(self, force: bool = False) -> Check:
         chk = Check()
         check(self.lib.pdlp_restart_check(self.h, int(bool(force)), C.byref(chk)))

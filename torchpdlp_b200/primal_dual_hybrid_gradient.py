@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import os
 import sys
+import threading
 import time
 
 import torch
@@ -139,7 +140,32 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
             trace_t.append((what, time.time()))
 
     lap("entry")
-    engine = _cache.engine_for(K, m_ineq, c, q, l, u, device)
+    # the power iteration's start vector is drawn from the global CPU generator (helpers.py:47 on a CPU device); 200k
+    # normal deviates take milliseconds, so they are drawn on a helper thread while the library builds the engine
+    # (both release the GIL; this is the only draw, so the generator is consumed exactly as in the sequential order)
+    draw = None
+    if b0 is None:
+        n_cols = int(K.shape[1]) if hasattr(K, "shape") else int(K[3][1])
+        b0_dtype = K.dtype if isinstance(K, torch.Tensor) and K.dtype in (torch.float32, torch.float64) else torch.float64
+        box = {}
+
+        def _draw():
+            try:
+                box["b0"] = torch.randn(n_cols, 1, dtype=b0_dtype)
+            except BaseException as err:      # re-raised on the caller's thread
+                box["err"] = err
+
+        draw = threading.Thread(target=_draw, name="pdlp-b0")
+        draw.start()
+    try:
+        engine = _cache.engine_for(K, m_ineq, c, q, l, u, device)
+    finally:
+        if draw is not None:
+            draw.join()
+    if draw is not None:
+        if "err" in box:
+            raise box["err"]
+        b0 = box["b0"].to(engine.dtype)
     lap("engine_for")
     scaled = bool(precondition)
     if precondition and data_precond is not None:
