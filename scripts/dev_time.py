@@ -6,7 +6,10 @@ from torchpdlp_b200 import synthetic
 from torchpdlp_b200.engine import Engine
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-lp = synthetic.make(name)
+if name == "cfg2even":      # config 2's shape with rows / columns that deal out evenly: 2 slices of K, 4 of K^T per warp
+    lp = synthetic.uniform_rows_lp(m_ineq=90_931, m_eq=22_733, n=227_328, name="cfg2even")
+else:
+    lp = synthetic.make(name)
 t0 = time.time()
 eng = Engine(lp.K, lp.m_ineq, lp.c, lp.q, lp.l, lp.u)
 torch.cuda.synchronize()

@@ -112,6 +112,27 @@ def test_two_gpu_solve_in_column_windows(monkeypatch):
 
 
 @needs_two
+@pytest.mark.parametrize("exchange,window_mb", [("nccl", None), ("p2p", None), ("nccl", "0.004")])
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_two_gpu_solve_on_dense_xbar(exchange, window_mb, adaptive, pw, monkeypatch):
+    """Row partition over two ranks with K_g xbar on the dense xbar vector (DualBarOp; config 5's default): the
+    element-wise / fused primal updates write xbar, K_g dx comes from the per-rank recursion on K_g x."""
+    monkeypatch.setenv("PDLP_XBAR", "1")
+    if window_mb:
+        monkeypatch.setenv("PDLP_WINDOW_MB", window_mb)
+    with open(os.path.join(GOLD, "cfg1_reference.json")) as f:
+        runs = json.load(f)["runs"]
+    gold = [r for r in runs if r["options"] == dict(ruiz=False, fishnet=False, adaptive=adaptive, primal_weight=pw)][0]["reference"]
+    res = run_world(exchange, adaptive, pw)
+    assert res["same_x"] and res["status"] == gold["status"] and res["n"] == gold["n"]
+    rel = abs(res["obj"] - gold["obj"]) / max(1.0, abs(gold["obj"]))
+    if adaptive:
+        assert abs(res["k"] - gold["k"]) <= 40 and rel < 1e-6, (res["k"], gold["k"], rel)
+    else:
+        assert (res["k"], res["j"]) == (gold["k"], gold["j"]) and rel < 1e-9
+
+
+@needs_two
 def test_two_gpu_exchanges_agree():
     """NCCL allreduce and the fused peer-memory exchange: the same solve (fixed step: bit for bit in k / n / j)."""
     a = run_world("nccl", False, False, "mid")

@@ -316,6 +316,41 @@ def test_cfg1_solve_in_column_windows(adaptive, pw, cfg1, monkeypatch):
         assert (k, j) == (gold["k"], gold["j"]) and rel(obj, gold["obj"]) < 1e-9
 
 
+@pytest.mark.parametrize("window_mb", [None, "0.004"], ids=["single_pass", "windows"])
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_cfg1_solve_on_dense_xbar(adaptive, pw, window_mb, cfg1, monkeypatch):
+    """K2 on the dense xbar vector (DualBarOp, forced through PDLP_XBAR=1; configs 4 and 5 use it because their
+    (x, dx) pair vector is beyond L2): 8-byte gathers, K dx from the recursion on K x.  Against the executed reference,
+    same bands as the pair kernels; K xbar is formed exactly as DualOp forms it, so with the fixed step (which never
+    looks at K dx) the single-pass solve equals the pair kernels' bit for bit.  Second case: in 4 column windows."""
+    gold = [r for r in CFG1_RUNS if r["options"] == dict(ruiz=False, fishnet=False, adaptive=adaptive, primal_weight=pw)][0]["reference"]
+    monkeypatch.setenv("PDLP_XBAR", "0")
+    x0, obj0, k0, n0, j0, status0, _, info0 = solve(cfg1, adaptive=adaptive, primal_weight=pw)
+    monkeypatch.setenv("PDLP_XBAR", "1")
+    if window_mb:
+        monkeypatch.setenv("PDLP_WINDOW_MB", window_mb)
+    x, obj, k, n, j, status, secs, info = solve(cfg1, adaptive=adaptive, primal_weight=pw)
+    assert status == gold["status"] and n == gold["n"]
+    if adaptive:
+        assert abs(k - gold["k"]) <= 40 and rel(obj, gold["obj"]) < ADAPTIVE_REL
+        assert abs(k - k0) <= 40 and rel(obj, obj0) < ADAPTIVE_REL
+    else:
+        assert (k, j) == (gold["k"], gold["j"]) and rel(obj, gold["obj"]) < 1e-9
+        if not window_mb:
+            assert torch.equal(x, x0) and torch.equal(info["y"], info0["y"])
+    # warm start from the solution (kx is recomputed from the new iterate), Ruiz on the same engine family, and the
+    # verbose host-driven loop (restart tests through pdlp_restart_check) take the same path
+    x2, obj2, k2, n2, j2, status2, *_ = solve(cfg1, ruiz=True, adaptive=adaptive, primal_weight=pw)
+    gold_r = [r for r in CFG1_RUNS if r["options"] == dict(ruiz=True, fishnet=False, adaptive=adaptive, primal_weight=pw)][0]["reference"]
+    assert status2 == gold_r["status"] and n2 == gold_r["n"]
+    if adaptive:
+        assert abs(k2 - gold_r["k"]) <= 40 and rel(obj2, gold_r["obj"]) < ADAPTIVE_REL
+    else:
+        assert (k2, j2) == (gold_r["k"], gold_r["j"]) and rel(obj2, gold_r["obj"]) < 1e-9
+    x3, obj3, k3, n3, j3, status3, *_ = solve(cfg1, adaptive=adaptive, primal_weight=pw, verbose=True)
+    assert (status3, n3) == (status, n) and abs(k3 - k) <= (40 if adaptive else 0) and rel(obj3, obj) < (ADAPTIVE_REL if adaptive else 1e-12)
+
+
 def test_cfg2_ruiz_full_size_against_oracle():
     """Ruiz on SPARSE K at full size (the reference cannot run it): oracle restatement,
     validated against the dense reference on config 1, vs the engine."""

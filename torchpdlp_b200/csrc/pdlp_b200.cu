@@ -9,6 +9,8 @@
 #include <cmath>
 #include <functional>
 #include <mutex>
+#include <queue>
+#include <utility>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -54,6 +56,7 @@ struct HostSell {
   int grid = 1;
   int max_piece_bytes = 16;
   int sigma = 0;                       // sorting window the cost model chose
+  int balanced = 0;                    // 1: slices dealt out to the warps longest-first (LPT) instead of contiguous ranges
 };
 
 static HostSell build_sell_plan(const int* rowptr, int rows, int value_bytes, int W, int KB, int sigma,
@@ -143,42 +146,146 @@ static HostSell build_sell_plan(const int* rowptr, int rows, int value_bytes, in
   while (order.size() % 32) order.push_back(-1);
   const int nsl_lane = (int)(order.size() / 32);
   for (int r : warp_rows) order.insert(order.end(), 32, r);       // a warp-row slice: the same row in all 32 lanes
-  P.perm = order;
-  const int nsl = (int)(order.size() / 32);
+  int nsl = (int)(order.size() / 32);
   std::vector<int> klen(nsl, 0);
+  std::vector<char> wr(nsl, 0), cut;                               // warp-row slice; LPT: a warp's range starts here
   for (int i = 0; i < nsl_lane; ++i)
     for (int r = 0; r < 32; ++r) {
       const int row = order[(size_t)i * 32 + r];
       if (row >= 0) klen[i] = std::max(klen[i], len(row));
     }
-  for (int i = nsl_lane; i < nsl; ++i) klen[i] = (len(order[(size_t)i * 32]) + 31) / 32;
-  std::vector<int> kbase;   // first step (position inside the row) covered by each piece
+  for (int i = nsl_lane; i < nsl; ++i) {
+    klen[i] = (len(order[(size_t)i * 32]) + 31) / 32;
+    wr[i] = 1;
+  }
   const int MAXSL = 16;     // StreamCfg::MAXSL
-  for (int i = 0; i < nsl;) {
-    if (klen[i] > KB || i >= nsl_lane) {
-      const uint32_t wr = i >= nsl_lane ? PIECE_WARP_ROW : 0u;
-      for (int k0 = 0; k0 < klen[i]; k0 += KB) {
-        Piece pc{0, i * 32, (uint16_t)std::min(KB, klen[i] - k0), 1,
-                 (k0 == 0 ? PIECE_FIRST : 0u) | (k0 + KB >= klen[i] ? PIECE_LAST : 0u) | wr};
+  std::vector<int> kbase;   // first step (position inside the row) covered by each piece
+  std::vector<int> piece_of_slice;
+  // pieces of the slices in their current order (short slices are merged, never across a cut)
+  auto make_pieces = [&]() {
+    P.pieces.clear();
+    kbase.clear();
+    piece_of_slice.assign((size_t)nsl, 0);
+    for (int i = 0; i < nsl;) {
+      piece_of_slice[i] = (int)P.pieces.size();
+      if (klen[i] > KB || wr[i]) {
+        const uint32_t w = wr[i] ? PIECE_WARP_ROW : 0u;
+        for (int k0 = 0; k0 < klen[i]; k0 += KB) {
+          Piece pc{0, i * 32, (uint16_t)std::min(KB, klen[i] - k0), 1,
+                   (k0 == 0 ? PIECE_FIRST : 0u) | (k0 + KB >= klen[i] ? PIECE_LAST : 0u) | w};
+          P.pieces.push_back(pc);
+          kbase.push_back(k0);
+        }
+        ++i;
+      } else {
+        int j = i, kmax = klen[i];
+        while (j + 1 < nsl && !wr[j + 1] && (cut.empty() || !cut[j + 1]) && (j + 1 - i) < MAXSL && klen[j + 1] <= KB &&
+               std::max(kmax, klen[j + 1]) * (j + 2 - i) <= KB) {
+          kmax = std::max(kmax, klen[j + 1]);
+          ++j;
+          piece_of_slice[j] = (int)P.pieces.size();
+        }
+        Piece pc{0, i * 32, (uint16_t)kmax, (uint16_t)(j - i + 1), PIECE_FIRST | PIECE_LAST};
         P.pieces.push_back(pc);
-        kbase.push_back(k0);
+        kbase.push_back(0);
+        i = j + 1;
       }
-      ++i;
-    } else {
-      int j = i, kmax = klen[i];
-      while (j + 1 < nsl_lane && (j + 1 - i) < MAXSL && klen[j + 1] <= KB &&
-             std::max(kmax, klen[j + 1]) * (j + 2 - i) <= KB) {
-        kmax = std::max(kmax, klen[j + 1]);
-        ++j;
+    }
+  };
+  // cost of a range of pieces: bytes + a fixed per-piece cost + the row epilogues
+  std::vector<double> pre;
+  auto prefix_costs = [&]() {
+    const int np = (int)P.pieces.size();
+    pre.assign((size_t)np + 1, 0.0);
+    for (int p = 0; p < np; ++p)
+      pre[p + 1] = pre[p] + (double)P.pieces[p].klen * P.pieces[p].nslices * 32 * (4 + value_bytes) + 256.0 +
+                   ((P.pieces[p].flags & PIECE_LAST) ? 32.0 * 40.0 * P.pieces[p].nslices : 0.0);
+  };
+  make_pieces();
+  prefix_costs();
+  int np = (int)P.pieces.size();
+  int starts = 0;
+  for (int p = 0; p < np; ++p) starts += (P.pieces[p].flags & PIECE_FIRST) ? 1 : 0;
+  P.grid = std::max(1, std::min(max_grid, (starts + W - 1) / W));
+  if (!P.long_rows.empty()) P.grid = std::max(P.grid, std::min(max_grid, (int)P.long_rows.size()));
+  const int nw = P.grid * W;
+  // warps: contiguous piece ranges balanced by cost, cut only where rows start
+  P.warp_begin.assign(nw + 1, np);
+  P.warp_begin[0] = 0;
+  for (int w = 1; w < nw; ++w) {
+    const double target = pre[np] * w / nw;
+    int lo = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+    lo = std::min(std::max(lo, P.warp_begin[w - 1]), np);
+    while (lo < np && !(P.pieces[lo].flags & PIECE_FIRST)) ++lo;
+    P.warp_begin[w] = lo;
+  }
+  P.warp_begin[nw] = np;
+  // Contiguous ranges can only be cut where rows start, so a warp may exceed its share by one slice -- for power-law
+  // rows up to 256 steps x 32 lanes (98 KB) against a share of a few hundred KB (config 4's K: the longest range was
+  // 1.41x the mean, and the kernel ran 1.43x longer than K^T's with the same bytes and sectors).  Where the window is
+  // wide anyway (no epilogue locality to keep) the slices are dealt out instead: longest first, each to the warp with
+  // the least work so far (LPT), the CTAs that start with a one-row-per-CTA giant handicapped by its cost; every warp's
+  // slices are then stored contiguously, in descending length, so short ones still merge into pieces.
+  {
+    double worst = 0.0;
+    for (int w = 0; w < nw; ++w) worst = std::max(worst, pre[P.warp_begin[w + 1]] - pre[P.warp_begin[w]]);
+    double giants = 0.0;
+    for (int r : P.long_rows) giants += (double)len(r) * (4 + value_bytes);
+    const double mean = (pre[np] + giants) / nw;
+    const bool lpt = sigma >= 1024 && nsl > nw && worst > 1.08 * mean && !getenv("PDLP_NO_LPT");
+    if (lpt) {
+      std::vector<double> cost((size_t)nsl);
+      for (int i = 0; i < nsl; ++i)
+        cost[i] = (double)klen[i] * 32 * (4 + value_bytes) + 256.0 * std::max(1.0 / MAXSL, (double)klen[i] / KB) + 32.0 * 40.0;
+      std::vector<int> by_cost((size_t)nsl);
+      for (int i = 0; i < nsl; ++i) by_cost[i] = i;
+      std::stable_sort(by_cost.begin(), by_cost.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      std::vector<double> load((size_t)nw, 0.0);
+      for (size_t li = 0; li < P.long_rows.size(); ++li) {           // long_rows_phase: row li goes to CTA li % grid
+        const int cta = (int)(li % (size_t)P.grid);
+        // straight from CSR, no ring: costed at twice its bytes, shared by the W warps of the CTA
+        for (int w = 0; w < W; ++w) load[(size_t)cta * W + w] += 2.0 * len(P.long_rows[li]) * (4 + value_bytes) / W;
       }
-      Piece pc{0, i * 32, (uint16_t)kmax, (uint16_t)(j - i + 1), PIECE_FIRST | PIECE_LAST};
-      P.pieces.push_back(pc);
-      kbase.push_back(0);
-      i = j + 1;
+      using Item = std::pair<double, int>;
+      std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+      for (int w = 0; w < nw; ++w) heap.push(Item{load[w], w});
+      std::vector<std::vector<int>> mine((size_t)nw);
+      for (int i : by_cost) {
+        Item it = heap.top();
+        heap.pop();
+        mine[(size_t)it.second].push_back(i);
+        it.first += cost[i];
+        heap.push(it);
+      }
+      std::vector<int> order2, klen2;
+      std::vector<char> wr2;
+      order2.reserve(order.size());
+      klen2.reserve((size_t)nsl);
+      wr2.reserve((size_t)nsl);
+      cut.assign((size_t)nsl + 1, 0);
+      std::vector<int> first_slice((size_t)nw + 1, 0);
+      for (int w = 0; w < nw; ++w) {
+        first_slice[w] = (int)klen2.size();
+        cut[klen2.size()] = 1;
+        for (int i : mine[(size_t)w]) {
+          order2.insert(order2.end(), order.begin() + (size_t)i * 32, order.begin() + (size_t)i * 32 + 32);
+          klen2.push_back(klen[i]);
+          wr2.push_back(wr[i]);
+        }
+      }
+      first_slice[nw] = nsl;
+      order.swap(order2);
+      klen.swap(klen2);
+      wr.swap(wr2);
+      make_pieces();
+      prefix_costs();
+      np = (int)P.pieces.size();
+      for (int w = 0; w <= nw; ++w) P.warp_begin[w] = first_slice[w] < nsl ? piece_of_slice[first_slice[w]] : np;
+      P.balanced = 1;
     }
   }
+  P.perm = order;
   // block offsets; the first step of a split slice's piece travels in the upper bits of flags (pack_kernel)
-  const int np = (int)P.pieces.size();
   size_t bytes = 0;
   for (int p = 0; p < np; ++p) {
     Piece& pc = P.pieces[p];
@@ -190,26 +297,12 @@ static HostSell build_sell_plan(const int* rowptr, int rows, int value_bytes, in
     bytes += pb;
   }
   P.packed_bytes = bytes;
-  // warps: contiguous piece ranges balanced by bytes (+ a fixed per-piece cost), cut only where rows start
-  std::vector<double> pre(np + 1, 0.0);
-  for (int p = 0; p < np; ++p)
-    pre[p + 1] = pre[p] + (double)P.pieces[p].klen * P.pieces[p].nslices * 32 * (4 + value_bytes) + 256.0 +
-                 ((P.pieces[p].flags & PIECE_LAST) ? 32.0 * 40.0 * P.pieces[p].nslices : 0.0);
-  int starts = 0;
-  for (int p = 0; p < np; ++p) starts += (P.pieces[p].flags & PIECE_FIRST) ? 1 : 0;
-  P.grid = std::max(1, std::min(max_grid, (starts + W - 1) / W));
-  if (!P.long_rows.empty()) P.grid = std::max(P.grid, std::min(max_grid, (int)P.long_rows.size()));
-  const int nw = P.grid * W;
-  P.warp_begin.assign(nw + 1, np);
-  P.warp_begin[0] = 0;
-  for (int w = 1; w < nw; ++w) {
-    const double target = pre[np] * w / nw;
-    int lo = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
-    lo = std::min(std::max(lo, P.warp_begin[w - 1]), np);
-    while (lo < np && !(P.pieces[lo].flags & PIECE_FIRST)) ++lo;
-    P.warp_begin[w] = lo;
+  if (getenv("PDLP_TRACE_SETUP")) {
+    double worst = 0.0;
+    for (int w = 0; w < nw; ++w) worst = std::max(worst, pre[P.warp_begin[w + 1]] - pre[P.warp_begin[w]]);
+    fprintf(stderr, "[pdlp setup] %d warps, %s ranges: longest %.0f KB, mean %.0f KB\n", nw,
+            P.balanced ? "dealt (LPT)" : "contiguous", worst / 1e3, pre[np] / nw / 1e3);
   }
-  P.warp_begin[nw] = np;
   return P;
 }
 
@@ -702,6 +795,13 @@ struct EngineT {
     std::vector<DeviceCsr<T>> M;
     Pair<T>* part = nullptr;
   } win;
+  // K2 on the dense xbar vector (DualBarOp, pdlp_ops.cuh): 8-byte gathers instead of (x, dx) pairs for operands whose
+  // pair vector does not stay L2-resident; K dx comes from the recursion on kx = K x.  `dirty`: kx must be recomputed
+  // from x before the next iteration (iterate or scaling set from outside, iterations that did not maintain it)
+  struct Bar {
+    bool on = false, dirty = true;
+    T *xb = nullptr, *kx = nullptr;
+  } bar;
 };
 
 // stream-ordered allocation from the device's default pool (kept cached: building an engine right after another
@@ -1038,7 +1138,8 @@ static int build_windows(EngineT<T>* E) {
   auto& W = E->win;
   const char* env = getenv("PDLP_WINDOW_MB");
   const double window_mb = env ? atof(env) : 64.0;
-  const double table_mb = (double)A.cols * sizeof(Pair<T>) / 1e6;
+  const size_t elem = E->bar.on ? sizeof(T) : sizeof(Pair<T>);       // what K2 gathers per column
+  const double table_mb = (double)A.cols * elem / 1e6;
   // a pair vector of about one window already misses L2 in 60 % of its gathers (config 4: 64 MB, measured): from
   // 0.9 windows on the matrix is cut in at least two
   if (window_mb <= 0.0 || table_mb <= 0.9 * window_mb) return 0;
@@ -1109,8 +1210,8 @@ static int build_windows(EngineT<T>* E) {
   CU(cudaStreamSynchronize(st));
   tr.lap("windows: plans + pack");
   if (getenv("PDLP_TRACE_SETUP"))
-    fprintf(stderr, "[pdlp setup] K in %d column windows of %d columns (%.0f MB of pairs each)\n", P, width,
-            (double)width * sizeof(Pair<T>) / 1e6);
+    fprintf(stderr, "[pdlp setup] K in %d column windows of %d columns (%.0f MB of %s each)\n", P, width,
+            (double)width * elem / 1e6, E->bar.on ? "xbar" : "pairs");
   return 0;
 }
 
@@ -1380,6 +1481,18 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
     if (rc) return rc;
   }
   if (E->k1 == 1 || E->k2 == 1 || E->Kt.run_on) tr.lap("run layout");
+  {
+    // dense-xbar K2 (DualBarOp): by default exactly where the pair vector would otherwise be cut into column windows
+    // (it does not stay L2-resident); PDLP_XBAR=1 / 0 forces it on / off.  SELL layout of K only.
+    const char* xenv = getenv("PDLP_XBAR");
+    const char* wenv = getenv("PDLP_WINDOW_MB");
+    const double window_mb = wenv ? atof(wenv) : 64.0;
+    const bool beyond = window_mb > 0.0 && (double)n * sizeof(Pair<T>) / 1e6 > 0.9 * window_mb;
+    E->bar.on = E->k2 == 0 && (xenv ? atoi(xenv) != 0 : beyond);
+    if (E->bar.on && getenv("PDLP_TRACE_SETUP"))
+      fprintf(stderr, "[pdlp setup] K2 gathers the dense xbar vector (%.1f MB) instead of (x, dx) pairs (%.1f MB)\n",
+              (double)n * sizeof(T) / 1e6, (double)n * sizeof(Pair<T>) / 1e6);
+  }
   rc = build_windows<T>(E);
   if (rc) return rc;
   if (E->k1 == 2) {
@@ -1395,6 +1508,11 @@ static int engine_create(pdlp_engine* B, const int32_t* K_rowptr, const int32_t*
   ALLOC(E->drow, m); ALLOC(E->dcol, n);
   ALLOC(E->tmp_n, n); ALLOC(E->tmp_m, m);
   ALLOC(E->kty_old, n); ALLOC(E->lam_prev, n);
+  if (E->bar.on) {
+    ALLOC(E->bar.xb, n); ALLOC(E->bar.kx, m);
+    CU(cudaMemsetAsync(E->bar.xb, 0, sizeof(T) * n, st));
+    CU(cudaMemsetAsync(E->bar.kx, 0, sizeof(T) * m, st));
+  }
   CU(cudaMemsetAsync(E->kty_old, 0, sizeof(T) * n, st));
   CU(cudaMemsetAsync(E->lam_prev, 0, sizeof(T) * n, st));
   ALLOC(E->S, 1);
@@ -1476,10 +1594,41 @@ static int refresh_norms(EngineT<T>* E) {
 // ---------------------------------------------------------------------------
 // hot loop
 // ---------------------------------------------------------------------------
-// K2 (K xbar + dual update + step rule) in whichever form the engine holds K: column windows (operand beyond L2; not
-// with infeasibility detection), the run layout, or SELL
+// kx = K x for DualBarOp: recomputed from the pair vector after a restart (after_restart = 1: the kernel looks at the
+// restart decision on the device and retires at once when there was none) or, after_restart = 0, unconditionally
+template <typename T>
+static cudaError_t launch_kx_refresh(EngineT<T>* E, int after_restart, cudaStream_t st) {
+  return launch_stream(E->K, KxRefreshOp<T>{E->xp, E->bar.kx, E->S, after_restart}, st);
+}
+// before iterations are issued: bring kx up to date if something outside the iteration kernels moved x or K
+template <typename T>
+static cudaError_t ensure_kx(EngineT<T>* E, cudaStream_t st) {
+  if (!E->bar.on || !E->bar.dirty) return cudaSuccess;
+  E->bar.dirty = false;
+  return launch_kx_refresh<T>(E, 0, st);
+}
+
+// K2 (K xbar + dual update + step rule) in whichever form the engine holds K: the dense xbar vector (DualBarOp, single
+// pass or column windows), column windows of pairs (operand beyond L2; not with infeasibility detection), the run
+// layout, or SELL
 template <typename T, bool SP, bool INF>
 static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st) {
+  if (!INF && E->bar.on) {
+    auto& W = E->win;
+    DualOp<T, SP, false> d{nullptr, E->q, E->y, E->ysum, E->Y4, E->S};
+    if (!W.on)
+      return launch_stream(E->K, DualBarOp<T, true, true, SP>{d, E->bar.xb, nullptr, E->bar.kx}, st, E->bar.xb,
+                           sizeof(T) * (size_t)E->base->n);
+    cudaError_t e = cudaSuccess;
+    T* part = reinterpret_cast<T*>(W.part);
+    for (int p = 0; p < W.P && e == cudaSuccess; ++p) {
+      const T* xb = E->bar.xb + W.begin[p];
+      if (p == 0) e = launch_stream(W.M[p], DualBarOp<T, true, false, SP>{d, xb, part, E->bar.kx}, st);
+      else if (p + 1 < W.P) e = launch_stream(W.M[p], DualBarOp<T, false, false, SP>{d, xb, part, E->bar.kx}, st);
+      else e = launch_stream(W.M[p], DualBarOp<T, false, true, SP>{d, xb, part, E->bar.kx}, st);
+    }
+    return e;
+  }
   if (!INF && E->win.on) {
     auto& W = E->win;
     cudaError_t e = cudaSuccess;
@@ -1500,6 +1649,7 @@ template <typename T, bool SP, bool INF>
 static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
   PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
   p.clu = E->clu;
+  p.xb = E->bar.xb;
   cudaError_t e;
   if (E->k1 == 2) e = launch_panel_combine<T>(E, p, (const T*)E->y, st);
   else if (E->k1 == 1) e = launch_run(E->Kt, p, st);
@@ -1597,7 +1747,9 @@ static int engine_iterate(EngineT<T>* E, int n_iters, int save_prev, int use_gra
   cudaStream_t st = B->stream;
   if (n_iters <= 0) return 0;
   if (save_prev) B->have_prev = true;
-  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0 && !E->win.on) {
+  if (B->infeas) E->bar.dirty = true;        // the kernels with the certificate sums gather pairs and leave kx alone
+  else CU(ensure_kx<T>(E, st));
+  if (use_graph == 2 && !B->infeas && E->k1 == 0 && E->k2 == 0 && !E->win.on && !E->bar.on) {
     // one persistent cooperative kernel for the whole block (SELL layout only; otherwise the CUDA graph below)
     const int grid = std::max(E->K.grid, E->Kt.grid);
     const int stages = std::min(E->K.nstages, E->Kt.nstages);
@@ -1629,9 +1781,11 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
   cudaStream_t st = E->base->stream;
   std::vector<cudaEvent_t> ev(3 * (size_t)n_iters);
   for (auto& e : ev) CU(cudaEventCreate(&e));
+  CU(ensure_kx<T>(E, st));
   for (int i = 0; i < n_iters; ++i) {
     PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
     p.clu = E->clu;
+    p.xb = E->bar.xb;
     CU(cudaEventRecord(ev[3 * i], st));
     if (E->k1 == 2) CU(launch_panel_combine<T>(E, p, (const T*)E->y, st));
     else if (E->k1 == 1) CU(launch_run(E->Kt, p, st));
@@ -1663,8 +1817,8 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
 template <typename T>
 static int engine_time_kernels_in_loop(EngineT<T>* E, int n_iters, float* primal_ms, float* dual_ms, float* iter_ms) {
   cudaStream_t st = E->base->stream;
-  if (E->k1 != 0 || E->k2 != 0 || E->win.on || E->base->infeas)
-    return fail(PDLP_ERR_STATE, "in-loop kernel timing covers the default (SELL, single pass) kernels only");
+  if (E->k1 != 0 || E->k2 != 0 || E->win.on || E->bar.on || E->base->infeas)
+    return fail(PDLP_ERR_STATE, "in-loop kernel timing covers the default (SELL, single pass, pair gathers) kernels only");
   if (n_iters < 1) return fail(PDLP_ERR_INVALID, "n_iters must be positive");
   unsigned long long* d = nullptr;
   CU(cudaMallocAsync((void**)&d, sizeof(unsigned long long) * 4 * (size_t)n_iters, st));
@@ -1735,6 +1889,7 @@ static void fill_check(pdlp_check* out, const Scalars& h) {
 // the cached restart-check graphs bake in the scaling state (pointers and the `scaled` flag): drop them when it changes
 template <typename T>
 static void drop_check_graphs(EngineT<T>* E) {
+  E->bar.dirty = true;                 // called whenever the scaling (hence K) changes: kx = K x is stale
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       if (E->check_graph[a][b]) cudaGraphExecDestroy(E->check_graph[a][b]);
@@ -1757,6 +1912,7 @@ static int enqueue_check(EngineT<T>* E, int force, int have_prev, cudaStream_t s
   decide_kernel<<<1, 1, 0, st>>>(E->S, force);
   apply_restart_kernel<T><<<E->ew_grid, 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, E->xlast, E->ylast,
                                                       n, m, E->S, E->ew_partials, E->ew_ticket);
+  if (E->bar.on) CU(launch_kx_refresh<T>(E, 1, st));       // kx = K x at the restart point (no-op without a restart)
   post_restart_kernel<<<1, 1, 0, st>>>(E->S, B->scaled ? 1 : 0);
   CU(cudaGetLastError());
   if (read_back) CU(cudaMemcpyAsync(E->h_scalars, E->S, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
@@ -2061,15 +2217,16 @@ static int shard_step(EngineT<T>* E, const double* buf, int save_prev) {
   pdlp_engine* B = E->base;
   cudaStream_t st = B->stream;
   const int n = (int)B->n;
+  CU(ensure_kx<T>(E, st));
   shard_rule_kernel<<<1, 1, 0, st>>>(E->S, buf + B->n);
   if (save_prev) {
     shard_primal_kernel<T, true><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
-                                                             E->ew_partials, E->ew_ticket);
+                                                             E->ew_partials, E->ew_ticket, E->bar.xb);
     CU((launch_dual<T, true, false>(E, st)));
     B->have_prev = true;
   } else {
     shard_primal_kernel<T, false><<<E->ew_grid, 256, 0, st>>>(buf, E->c, E->l, E->u, E->xp, E->xsum, E->X4, n, E->S,
-                                                              E->ew_partials, E->ew_ticket);
+                                                              E->ew_partials, E->ew_ticket, E->bar.xb);
     CU((launch_dual<T, false, false>(E, st)));
   }
   CU(cudaGetLastError());
@@ -2190,6 +2347,7 @@ static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
   if (E->Kt.grid > B->sms) return fail(PDLP_ERR_STATE, "the fused exchange needs a co-resident grid");
   CU(ensure_smem_attr(shard_fused_kernel<T, true>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
   CU(ensure_smem_attr(shard_fused_kernel<T, false>, StreamCfg<T>::MAX_SMEM_BYTES - 4096));
+  CU(ensure_kx<T>(E, st));
   for (int i = 0; i < n_iters; ++i) {
     const bool save = save_prev && i == n_iters - 1;
     // column side: SpMV + exchange + step rule + primal update in ONE kernel; row side: the ordinary DualOp
@@ -2199,12 +2357,14 @@ static int shard_iterate_p2p(EngineT<T>* E, int n_iters, int save_prev) {
     const Xchg* xd = B->xchg_dev;
     if (save) {
       CU(cudaLaunchKernelEx(&cfg, shard_fused_kernel<T, true>, E->Kt.view(), xd, (const T*)E->y, (const T*)E->c,
-                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
+                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket,
+                            E->bar.xb));
       CU((launch_dual<T, true, false>(E, st)));
       B->have_prev = true;
     } else {
       CU(cudaLaunchKernelEx(&cfg, shard_fused_kernel<T, false>, E->Kt.view(), xd, (const T*)E->y, (const T*)E->c,
-                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket));
+                            (const T*)E->l, (const T*)E->u, E->xp, E->xsum, E->X4, E->S, E->ew_partials, E->ew_ticket,
+                            E->bar.xb));
       CU((launch_dual<T, false, false>(E, st)));
     }
     CU(cudaGetLastError());
@@ -2247,6 +2407,7 @@ static int shard_check_decide(EngineT<T>* E, const double* buf9, int force, doub
   decide_kernel<<<1, 1, 0, st>>>(E->S, force);
   apply_restart_kernel<T><<<E->ew_grid, 256, 0, st>>>(E->xp, E->y, E->xsum, E->ysum, E->X4, E->Y4, E->xlast, E->ylast,
                                                       (int)B->n, (int)B->m, E->S, E->ew_partials, E->ew_ticket);
+  if (E->bar.on) CU(launch_kx_refresh<T>(E, 1, st));
   shard_dy_pack_kernel<<<1, 1, 0, st>>>(E->S, buf1);
   CU(cudaGetLastError());
   return 0;
@@ -2829,6 +2990,7 @@ static int t_set_iterate(EngineT<T>* E, const void* x, const void* y) {
   set_iterate_kernel<T><<<ew_blocks(std::max(m, n), B->sms), 256, 0, B->stream>>>(
       (const T*)x, (const T*)y, E->xp, E->y, E->xsum, E->ysum, E->xlast, E->ylast, n, m);
   CU(cudaGetLastError());
+  E->bar.dirty = true;
   // :58-64 / :104-112: fresh epoch
   const double z[2] = {0.0, 0.0};
   CU(cudaMemcpyAsync((char*)E->S + offsetof(Scalars, w_pending), z, 2 * sizeof(double), cudaMemcpyHostToDevice, B->stream));

@@ -204,11 +204,14 @@ struct PrimalOp {
   bool do_save = true;   // runtime gate of SAVE_PREV (the persistent kernel saves only on its last iteration)
   const Quad<T>* clu = nullptr;   // (c, l, u, 0) records: one 32-byte sector per row instead of three (sigma-sorted rows
                                   // make every epilogue access its own sector, section 4b of DESIGN.md)
+  T* xb = nullptr;                // dense xbar = x' + theta dx for DualBarOp (8-byte gathers), null otherwise
+  T theta = T(1);
   __device__ bool begin() {
     if (S->stop) return false;
     tau = (T)(S->eta / S->omega);
     wpend = (T)S->w_pending;
     itol = (T)S->infeas_tol;
+    theta = (T)S->theta;
     return true;
   }
   __device__ T gather(int col) const { return ldg_keep(y + col); }
@@ -225,6 +228,7 @@ struct PrimalOp {
     const T xn = clampv(k.xo - tau * g, k.l, k.u);
     const T dx = xn - k.xo;
     xp[j] = Pair<T>{xn, dx};
+    if (xb) xb[j] = xn + theta * dx;          // the value DualOp::mac forms from the pair
     xsum[j] = k.xs + wpend * k.xo;
     if (SAVE_PREV && do_save) X4[j].v[IT_PREV] = k.xo;
     red[0] += (double)dx * (double)dx;
@@ -365,6 +369,85 @@ struct DualWindowOp {
   __device__ void finalize(const double (&tot)[NRED > 0 ? NRED : 1]) {
     if constexpr (LAST) d.finalize(tot);
   }
+};
+
+// ---------------------------------------------------------------------------
+// K2 on the dense xbar vector (operands beyond L2: configs 4 and 5).  The (x, dx) pair costs 16 bytes per column of
+// L2 footprint only so that K dx -- needed by the adaptive rule's dy^T K dx -- comes out of the same gather.  Here
+// K1 also writes xbar = x' + theta dx as a dense vector (PrimalOp::xb), K2 gathers 8 bytes (half the table: config 4's
+// 32 MB stay L2-resident where 64 MB of pairs do not), forms u = K xbar exactly as DualOp does -- so the dual update
+// is the same to the bit -- and takes K dx from the recursion on v = K x kept per row:
+//     xbar = (1 + theta) x' - theta x   =>   K dx = (u - v) / (1 + theta),   v' = K x' = v + K dx.
+// An error in v is damped by theta / (1 + theta) per iteration; v is recomputed from x at every restart and whenever
+// the iterate or the scaling is set from outside (KxRefreshOp).  In column windows (FIRST / LAST as DualWindowOp) the
+// carried partial sum is one value per row instead of a pair.
+// ---------------------------------------------------------------------------
+template <typename T, bool FIRST, bool LAST, bool SAVE_PREV>
+struct DualBarOp {
+  using value_type = T;
+  using Gather = T;
+  using Inner = DualOp<T, SAVE_PREV, false>;
+  struct Ctx { T part, kx; typename Inner::Ctx in; };
+  static constexpr int NV = 1;
+  static constexpr int NRED = LAST ? Inner::NRED : 0;
+  static constexpr int UDIV = 1;
+  static constexpr int PIPE = 1;
+  Inner d;               // d.xp is not used
+  const T* xb;           // already points at the window's first column
+  T* part;
+  T* kx;
+  T inv1t = T(1);
+  __device__ bool begin() {
+    if (!d.begin()) return false;
+    inv1t = T(1) / (T(1) + d.theta);
+    return true;
+  }
+  __device__ T gather(int col) const { return ldg_keep(xb + col); }
+  __device__ void mac(T (&acc)[1], T a, const T& g) const { acc[0] += a * g; }
+  __device__ Ctx row_load(int i) const {
+    Ctx c;
+    if (!FIRST) c.part = ldg(part + i);
+    if (LAST) { c.kx = kx[i]; c.in = d.row_load(i); }
+    return c;
+  }
+  __device__ void row_finish(int i, const Ctx& k, const T (&acc)[1], double (&red)[NRED > 0 ? NRED : 1]) {
+    T u = acc[0];
+    if (!FIRST) u = k.part + u;
+    if constexpr (LAST) {
+      const T kdx = (u - k.kx) * inv1t;
+      kx[i] = k.kx + kdx;
+      const T a[2] = {u, kdx};
+      d.row_finish(i, k.in, a, red);
+    } else {
+      part[i] = u;
+    }
+  }
+  __device__ void finalize(const double (&tot)[NRED > 0 ? NRED : 1]) {
+    if constexpr (LAST) d.finalize(tot);
+  }
+};
+
+// v = K x from the pair vector (full K): after a restart (conditional: nothing to do when the test did not restart or
+// the solve has stopped) and when the iterate or the scaling was set from outside
+template <typename T>
+struct KxRefreshOp {
+  using value_type = T;
+  using Gather = Pair<T>;
+  using Ctx = NoCtx;
+  static constexpr int NV = 1;
+  static constexpr int NRED = 0;
+  static constexpr int UDIV = 1;
+  static constexpr int PIPE = 0;
+  const Pair<T>* xp;
+  T* kx;
+  const Scalars* S;
+  int after_restart;
+  __device__ bool begin() { return !(after_restart && (S->stop || S->chk_kind == 0)); }
+  __device__ Pair<T> gather(int col) const { return ldg(xp + col); }
+  __device__ void mac(T (&acc)[1], T a, const Pair<T>& p) const { acc[0] += a * p.a; }
+  __device__ Ctx row_load(int) const { return Ctx{}; }
+  __device__ void row_finish(int i, const Ctx&, const T (&acc)[1], double (&)[1]) { kx[i] = acc[0]; }
+  __device__ void finalize(const double (&)[1]) {}
 };
 
 // ---------------------------------------------------------------------------
@@ -854,10 +937,11 @@ __global__ void __launch_bounds__(256) xchg_allreduce_kernel(const Xchg* Xp, Sca
 // element-wise K1 epilogue on the allreduced K^T y (same arithmetic as PrimalOp::row_finish)
 template <typename T, bool SAVE_PREV>
 __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, const T* u, Pair<T>* xp, T* xsum,
-                                    Quad<T>* X4, int n, Scalars* S, double* partials, unsigned int* ticket) {
+                                    Quad<T>* X4, int n, Scalars* S, double* partials, unsigned int* ticket, T* xb) {
   if (S->stop) return;
   const T tau = (T)(S->eta / S->omega);
   const T wpend = (T)S->w_pending;
+  const T theta = (T)S->theta;
   const int stride = gridDim.x * blockDim.x;
   double dx2 = 0.0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
@@ -866,6 +950,7 @@ __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, c
     const T xn = clampv(xo - tau * g, l[j], u[j]);
     const T dx = xn - xo;
     xp[j] = Pair<T>{xn, dx};
+    if (xb) xb[j] = xn + theta * dx;
     xsum[j] += wpend * xo;
     if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
     dx2 += (double)dx * (double)dx;
@@ -902,7 +987,8 @@ __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, c
 template <typename T, bool SAVE_PREV, bool ONESHOT>
 __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned int seq, const T* c, const T* l, const T* u,
                                                         Pair<T>* xp, T* xsum, Quad<T>* X4, Scalars* S, double* partials,
-                                                        unsigned int* ticket, double* sh, double* s_rule, int* s_int) {
+                                                        unsigned int* ticket, double* sh, double* s_rule, int* s_int,
+                                                        T* xb) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthr = gridDim.x * blockDim.x;
   if (!ONESHOT) xchg_reduce_owned(X, X.L, seq, S, tid, nthr);
@@ -936,6 +1022,7 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
   if (!s_stop) {
     const T tau = (T)(s_rule[0] / S->omega);
     const T wpend = (T)s_rule[1];
+    const T theta = (T)S->theta;
     const uint4* col = tot + XCHG_TAIL;
     const uint4* col1 = tot1 + XCHG_TAIL;
     constexpr int NB = 4;
@@ -963,6 +1050,7 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
           const T xn = clampv(xo - tau * g, lj[b], uj[b]);
           const T dx = xn - xo;
           xp[j] = Pair<T>{xn, dx};
+          if (xb) xb[j] = xn + theta * dx;
           xsum[j] = sj[b] + wpend * xo;
           if (SAVE_PREV) X4[j].v[IT_PREV] = xo;
           dx2 += (double)dx * (double)dx;
@@ -1042,7 +1130,7 @@ struct ShardPushOp {
 template <typename T, bool SAVE_PREV>
 __global__ void __launch_bounds__(StreamCfg<T>::NT, 1)
 shard_fused_kernel(const SellView<T> A, const Xchg* Xp, const T* y, const T* c, const T* l, const T* u, Pair<T>* xp,
-                   T* xsum, Quad<T>* X4, Scalars* S, double* partials, unsigned int* ticket) {
+                   T* xsum, Quad<T>* X4, Scalars* S, double* partials, unsigned int* ticket, T* xb) {
   using Cfg = StreamCfg<T>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[Cfg::W][Cfg::SMAX];
@@ -1086,9 +1174,9 @@ shard_fused_kernel(const SellView<T> A, const Xchg* Xp, const T* y, const T* c, 
   double red[1] = {0.0};
   stream_phase<ShardPushOp<T>, 1>(A, op, red, R, pb, pe, s_red);
   if (X.oneshot)
-    xchg_reduce_rule_primal<T, SAVE_PREV, true>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
+    xchg_reduce_rule_primal<T, SAVE_PREV, true>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int, xb);
   else
-    xchg_reduce_rule_primal<T, SAVE_PREV, false>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int);
+    xchg_reduce_rule_primal<T, SAVE_PREV, false>(X, seq, c, l, u, xp, xsum, X4, S, partials, ticket, sh, s_rule, s_int, xb);
 }
 
 // element-wise KKT column side on the allreduced K^T Y4 (same arithmetic as KktColsOp::row_finish); one block
