@@ -1611,11 +1611,19 @@ static cudaError_t ensure_kx(EngineT<T>* E, cudaStream_t st) {
 // K2 (K xbar + dual update + step rule) in whichever form the engine holds K: the dense xbar vector (DualBarOp, single
 // pass or column windows), column windows of pairs (operand beyond L2; not with infeasibility detection), the run
 // layout, or SELL
+// dx2_deferred: the PrimalOp before this launch left ||dx||^2 as per-CTA partial sums (primal_defers)
 template <typename T, bool SP, bool INF>
-static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st) {
+static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st, bool dx2_deferred = false) {
+  auto take_dx2 = [&](auto& d) {
+    if (dx2_deferred) {
+      d.dx2_partials = E->Kt.partials;
+      d.dx2_blocks = E->Kt.grid;
+    }
+  };
   if (!INF && E->bar.on) {
     auto& W = E->win;
     DualOp<T, SP, false> d{nullptr, E->q, E->y, E->ysum, E->Y4, E->S};
+    take_dx2(d);
     if (!W.on)
       return launch_stream(E->K, DualBarOp<T, true, true, SP>{d, E->bar.xb, nullptr, E->bar.kx}, st, E->bar.xb,
                            sizeof(T) * (size_t)E->base->n);
@@ -1634,6 +1642,7 @@ static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     for (int p = 0; p < W.P && e == cudaSuccess; ++p) {
       DualOp<T, SP, false> d{E->xp + W.begin[p], E->q, E->y, E->ysum, E->Y4, E->S};
+      take_dx2(d);
       if (p == 0) e = launch_stream(W.M[p], DualWindowOp<T, true, false, SP>{d, W.part}, st);
       else if (p + 1 < W.P) e = launch_stream(W.M[p], DualWindowOp<T, false, false, SP>{d, W.part}, st);
       else e = launch_stream(W.M[p], DualWindowOp<T, false, true, SP>{d, W.part}, st);
@@ -1641,8 +1650,16 @@ static cudaError_t launch_dual(EngineT<T>* E, cudaStream_t st) {
     return e;
   }
   DualOp<T, SP, INF> d{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+  take_dx2(d);
   if (E->k2 == 1) return launch_run(E->K, d, st);
   return launch_stream(E->K, d, st, E->xp, sizeof(Pair<T>) * (size_t)E->base->n);
+}
+
+// K1's grid reduction can be left to K2's finalize when both run in stream_kernel (SELL layouts) and K1's finalize
+// stores nothing else (no infeasibility detection)
+template <typename T>
+static bool primal_defers(const EngineT<T>* E, bool inf) {
+  return !inf && E->k1 == 0 && E->k2 == 0 && !getenv("PDLP_NO_DEFER");
 }
 
 template <typename T, bool SP, bool INF>
@@ -1650,12 +1667,13 @@ static cudaError_t enqueue_one(EngineT<T>* E, cudaStream_t st) {
   PrimalOp<T, SP, INF> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
   p.clu = E->clu;
   p.xb = E->bar.xb;
+  p.defer = primal_defers<T>(E, INF);
   cudaError_t e;
   if (E->k1 == 2) e = launch_panel_combine<T>(E, p, (const T*)E->y, st);
   else if (E->k1 == 1) e = launch_run(E->Kt, p, st);
   else e = launch_stream(E->Kt, p, st, E->y, sizeof(T) * (size_t)E->base->m);
   if (e != cudaSuccess) return e;
-  e = launch_dual<T, SP, INF>(E, st);
+  e = launch_dual<T, SP, INF>(E, st, p.defer);
   if (e != cudaSuccess) return e;
   if (INF) {
     InfeasColsOp<T> f{E->y, E->c, E->l, E->u, E->kty_old, E->lam_prev, E->S};
@@ -1786,12 +1804,13 @@ static int engine_time_kernels(EngineT<T>* E, int n_iters, float* primal_ms, flo
     PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
     p.clu = E->clu;
     p.xb = E->bar.xb;
+    p.defer = primal_defers<T>(E, false);
     CU(cudaEventRecord(ev[3 * i], st));
     if (E->k1 == 2) CU(launch_panel_combine<T>(E, p, (const T*)E->y, st));
     else if (E->k1 == 1) CU(launch_run(E->Kt, p, st));
     else CU(launch_stream(E->Kt, p, st));
     CU(cudaEventRecord(ev[3 * i + 1], st));
-    CU((launch_dual<T, false, false>(E, st)));
+    CU((launch_dual<T, false, false>(E, st, p.defer)));
     CU(cudaEventRecord(ev[3 * i + 2], st));
   }
   CU(cudaStreamSynchronize(st));
@@ -1830,9 +1849,14 @@ static int engine_time_kernels_in_loop(EngineT<T>* E, int n_iters, float* primal
   for (int i = 0; i < n_iters && err == cudaSuccess; ++i) {
     PrimalOp<T, false, false> p{E->y, E->c, E->l, E->u, E->xp, E->xsum, E->X4, E->S, E->kty_old};
     p.clu = E->clu;
+    p.defer = primal_defers<T>(E, false);
     err = launch_stream(E->Kt, p, st, nullptr, 0, d + 4 * (size_t)i);
     if (err != cudaSuccess) break;
     DualOp<T, false, false> q{E->xp, E->q, E->y, E->ysum, E->Y4, E->S};
+    if (p.defer) {
+      q.dx2_partials = E->Kt.partials;
+      q.dx2_blocks = E->Kt.grid;
+    }
     err = launch_stream(E->K, q, st, nullptr, 0, d + 4 * (size_t)i + 2);
   }
   if (err == cudaSuccess) err = cudaEventRecord(e1, st);

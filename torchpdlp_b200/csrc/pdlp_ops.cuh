@@ -206,6 +206,8 @@ struct PrimalOp {
                                   // make every epilogue access its own sector, section 4b of DESIGN.md)
   T* xb = nullptr;                // dense xbar = x' + theta dx for DualBarOp (8-byte gathers), null otherwise
   T theta = T(1);
+  bool defer = false;             // stop after the per-CTA partial ||dx||^2: the DualOp that follows adds them up
+                                  // (DualOp::dx2_partials); not with INFEAS, whose finalize stores more
   __device__ bool begin() {
     if (S->stop) return false;
     tau = (T)(S->eta / S->omega);
@@ -271,6 +273,18 @@ struct DualOp {
   T sigma, theta, wpend, itol;
   int m_ineq;
   bool do_save = true;
+  // ||dx||^2 left as per-CTA partial sums by a PrimalOp with `defer` (its kernel's block_partials, stride MAX_RED):
+  // summed here in grid_totals' fixed order, by the warp that runs the finalize; null: Scalars::dx2 is current
+  const double* dx2_partials = nullptr;
+  int dx2_blocks = 0;
+  double dx2_tot = 0.0;
+  __device__ void pre_finalize() {
+    if (dx2_partials) {
+      double t[1];
+      grid_totals<1>(dx2_partials, MAX_RED, dx2_blocks, t);
+      dx2_tot = t[0];
+    }
+  }
   __device__ bool begin() {
     if (S->stop) return false;
     sigma = (T)(S->eta * S->omega);
@@ -309,6 +323,7 @@ struct DualOp {
   // step.py:96-115 (adaptive) / :40 (fixed) and primal_dual_hybrid_gradient.py:104-112
   __device__ void finalize(const double (&tot)[NRED]) {
     Scalars& s = *S;
+    if (dx2_partials) s.dx2 = dx2_tot;
     s.dy2 = tot[0];
     s.inter = tot[1];
     if (s.sharded) {          // partial sums: the rule runs after the host allreduce (shard_rule_kernel)
@@ -366,6 +381,9 @@ struct DualWindowOp {
     if constexpr (LAST) d.row_finish(i, k.in, a, red);
     else part[i] = Pair<T>{a[0], a[1]};
   }
+  __device__ void pre_finalize() {
+    if constexpr (LAST) d.pre_finalize();
+  }
   __device__ void finalize(const double (&tot)[NRED > 0 ? NRED : 1]) {
     if constexpr (LAST) d.finalize(tot);
   }
@@ -421,6 +439,9 @@ struct DualBarOp {
     } else {
       part[i] = u;
     }
+  }
+  __device__ void pre_finalize() {
+    if constexpr (LAST) d.pre_finalize();
   }
   __device__ void finalize(const double (&tot)[NRED > 0 ? NRED : 1]) {
     if constexpr (LAST) d.finalize(tot);

@@ -20,6 +20,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+#include <utility>
+
 namespace pdlp {
 
 #ifndef PDLP_W
@@ -454,6 +457,17 @@ __device__ __forceinline__ void grid_totals(const double* partials, int stride, 
   }
 }
 
+// Optional members of an op, detected here:
+//   bool defer;                 true: the kernel stops after the per-CTA partial sums (no ticket, no finalize) -- the
+//                               next kernel's op adds them up itself (PrimalOp -> DualOp: ||dx||^2 is only needed by the
+//                               step rule, so K1's tail loses an atomic round trip, a re-read and a dependent store)
+//   void pre_finalize();        run by the whole first warp of the last CTA before lane 0 calls finalize
+template <class Op, class = void> struct op_has_defer : std::false_type {};
+template <class Op> struct op_has_defer<Op, std::void_t<decltype(std::declval<const Op&>().defer)>> : std::true_type {};
+template <class Op, class = void> struct op_has_pre_finalize : std::false_type {};
+template <class Op>
+struct op_has_pre_finalize<Op, std::void_t<decltype(std::declval<Op&>().pre_finalize())>> : std::true_type {};
+
 template <class Op>
 __global__ void __launch_bounds__(StreamCfg<typename Op::value_type>::NT, StreamCfg<typename Op::value_type>::MINB)
 stream_kernel(const SellView<typename Op::value_type> A, Op op) {
@@ -510,6 +524,16 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
   // ---------------- deterministic grid reduction + finalize ----------------
   if constexpr (NRED > 0) {
     block_reduce<NRED, SR>(red, s_red, &A.block_partials[(size_t)blockIdx.x * MAX_RED]);
+    if constexpr (op_has_defer<Op>::value) {
+      if (op.defer) {
+        if (A.stamp && tid == 0) {      // timing run: the latest CTA's clock is the end of the launch
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          atomicMax(A.stamp + 1, now);
+        }
+        return;
+      }
+    }
     if (tid == 0) {
       __threadfence();
       const unsigned int ticket = atomicAdd(A.ticket, 1u);
@@ -520,6 +544,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
       __threadfence();
       double tot[NR];
       grid_totals<NRED>(A.block_partials, MAX_RED, (int)gridDim.x, tot);
+      if constexpr (op_has_pre_finalize<Op>::value) op.pre_finalize();
       if (lane == 0) {
         op.finalize(tot);
         *A.ticket = 0u;
