@@ -69,6 +69,34 @@ def test_power_law_rows_get_a_wide_window_and_three_classes():
     assert info.max_warp_bytes <= 1.25 * info.mean_warp_bytes + 8192 * 12 + 4096
 
 
+def test_wide_windows_deal_slices_out_longest_first(monkeypatch):
+    """Config 4's K at 1/4 scale (power-law rows up to 100 000 entries): contiguous per-warp ranges can only be cut
+    where rows start, so a warp overshoots its share by up to one slice of 256 steps (98 KB) -- on the GPU the kernel
+    then runs as long as its most loaded warp (config 4: K2 433 us against K1's 297 us for the same bytes).  With a wide
+    sorting window (no epilogue locality to keep) the planner deals the slices out longest-first instead: every
+    invariant holds and the longest range is within a few percent of the mean; PDLP_NO_LPT=1 restores the ranges."""
+    lp = synthetic.powerlaw_rows_lp(400_000, 100_000, 1_000_000, seed=0, name="pl4")
+    lens = np.diff(lp.K.indptr)
+    monkeypatch.setenv("PDLP_NO_LPT", "1")
+    before, cls = inspect(lens)
+    check_invariants(lens, before, cls)
+    monkeypatch.delenv("PDLP_NO_LPT")
+    after, cls = inspect(lens)
+    check_invariants(lens, after, cls)
+    assert before.sigma >= 1024 and after.sigma == before.sigma
+    assert before.max_warp_bytes > 1.2 * before.mean_warp_bytes          # the problem is there ...
+    # ... and gone: within a few percent of the mean, or one indivisible unit (a slice of 256 steps x 32 lanes / a warp
+    # row of 8192 entries, 98 KB + headers) where the mean itself is below that (this 1/4-scale matrix)
+    assert after.max_warp_bytes <= max(1.06 * after.mean_warp_bytes, 256 * 32 * 12 + 4096)
+    assert after.max_warp_bytes < 0.8 * before.max_warp_bytes
+    assert after.slots <= 1.01 * before.slots                            # same padding (merging of short slices kept)
+    # uniform rows keep their contiguous ranges (narrow window: consecutive slices share epilogue cache lines)
+    u0, _ = inspect(np.full(100_000, 50))
+    monkeypatch.setenv("PDLP_NO_LPT", "1")
+    u1, _ = inspect(np.full(100_000, 50))
+    assert (u0.pieces, u0.max_warp_bytes, u0.packed_bytes) == (u1.pieces, u1.max_warp_bytes, u1.packed_bytes)
+
+
 @pytest.mark.parametrize("lens", [[], [0], [0, 0, 0], [1], [257], [8193], [5, 0, 300, 0, 9000, 1, 256, 8192]])
 def test_edge_cases(lens):
     info, cls = inspect(lens)
