@@ -17,7 +17,7 @@ SOURCES = [os.path.join(HERE, "csrc", "pdlp_b200.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("stream_spmv.cuh", "run_spmv.cuh", "panel_spmv.cuh", "pdlp_ops.cuh", "pdlp_block.cuh")] + \
           [os.path.join(ROOT, "include", "pdlp_b200.h")]
 
-NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-O3", "-std=c++17"]
 
 

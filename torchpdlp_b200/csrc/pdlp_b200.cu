@@ -13,6 +13,7 @@
 #include <utility>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -737,6 +738,33 @@ static void pinned_scalars_put(void* p) {
   std::lock_guard<std::mutex> lock(g_pinned_mutex);
   g_pinned_free.push_back(p);
 }
+// pinned staging buffers of arbitrary size (host ingest: the column counts come back while the transpose still runs);
+// recycled across engines like the read-back buffers above -- cudaMallocHost costs a fraction of a millisecond
+static std::vector<std::pair<void*, size_t>> g_pinned_bufs;
+static void* pinned_buf_get(size_t bytes, size_t* cap) {
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    for (size_t i = 0; i < g_pinned_bufs.size(); ++i)
+      if (g_pinned_bufs[i].second >= bytes) {
+        void* p = g_pinned_bufs[i].first;
+        *cap = g_pinned_bufs[i].second;
+        g_pinned_bufs.erase(g_pinned_bufs.begin() + (long)i);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  *cap = bytes;
+  return p;
+}
+static void pinned_buf_put(void* p, size_t cap) {
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  if (g_pinned_bufs.size() < 4) g_pinned_bufs.emplace_back(p, cap);
+  else cudaFreeHost(p);
+}
 
 template <typename T>
 struct EngineT {
@@ -1394,7 +1422,7 @@ static int ingest_host_csr(EngineT<T>* E, const void* h_rowptr, const void* h_co
   // H2D: pinned sources are DMA'd asynchronously (the host plans K meanwhile), pageable ones are staged by the driver
   CUT(cudaMemcpyAsync(K.rowptr, K.h_rowptr.data(), sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, st));
   CUT(cudaMemcpyAsync(raw_col, h_colidx, (size_t)nnz * (size_t)index_bytes, cudaMemcpyHostToDevice, st));
-  CUT(cudaMemcpyAsync(K.vals, h_vals, sizeof(T) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+  // (the values follow further down: the column counts, which the K^T plan waits for, need the indices only)
   CUT(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), st));
   CUT(cudaMemsetAsync(err, 0, sizeof(int) * 2, st));
   if (nnz > 0) {
@@ -1406,6 +1434,20 @@ static int ingest_host_csr(EngineT<T>* E, const void* h_rowptr, const void* h_co
     CUT(cudaGetLastError());
   }
   CUT(cub::DeviceScan::ExclusiveSum(cub_tmp, scan_bytes, cnt, Kt.rowptr, n + 1, st));
+  // K^T's row pointers are final here, long before the transpose itself: they come back through a pinned buffer and
+  // a helper thread plans K^T from them while this thread plans K (both are host work of a millisecond or two)
+  size_t pin_cap = 0;
+  int* pin_rowptr = (int*)pinned_buf_get(sizeof(int) * ((size_t)n + 1), &pin_cap);
+  cudaEvent_t ev_counts = nullptr;
+  if (pin_rowptr && cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming) == cudaSuccess) {
+    if (cudaMemcpyAsync(pin_rowptr, Kt.rowptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaEventRecord(ev_counts, st) != cudaSuccess) {
+      cudaGetLastError();
+      cudaEventDestroy(ev_counts);
+      ev_counts = nullptr;
+    }
+  }
+  CUT(cudaMemcpyAsync(K.vals, h_vals, sizeof(T) * (size_t)nnz, cudaMemcpyHostToDevice, st));
   if (nnz > 0) {
     CUT(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, (const int*)K.colidx, keys_out, (const int*)idx, perm, nnz, 0, end_bit, st));
     const int blocks = (int)std::min<int64_t>(((int64_t)nnz + 255) / 256, (int64_t)B->sms * 32);
@@ -1413,14 +1455,33 @@ static int ingest_host_csr(EngineT<T>* E, const void* h_rowptr, const void* h_co
     CUT(cudaGetLastError());
   }
   tr.lap("host csr: copies + kernels issued");
+  Kt.h_rowptr.resize((size_t)n + 1);
+  HostSell PT;
+  bool planned_t = false;
+  std::thread helper;
+  if (ev_counts && !getenv("PDLP_NO_PLAN_THREAD")) {
+    const int device = B->device;
+    helper = std::thread([&, device]() {
+      if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(ev_counts) != cudaSuccess) return;
+      memcpy(Kt.h_rowptr.data(), pin_rowptr, sizeof(int) * ((size_t)n + 1));
+      if (Kt.h_rowptr[(size_t)n] != nnz) return;        // reported below, from the main thread
+      PT = plan_csr<T>(E, Kt);
+      planned_t = true;
+    });
+  }
   // while the device copies and transposes: plan K on the host
   HostSell PK = plan_csr<T>(E, K);
   tr.lap("plan K (host, overlapped)");
+  if (helper.joinable()) helper.join();
+  tr.lap("plan K^T (helper thread, overlapped)");
+  if (ev_counts) cudaEventDestroy(ev_counts);
   int h_err[2] = {0, 0};
-  Kt.h_rowptr.resize((size_t)n + 1);
-  CUT(cudaMemcpyAsync(Kt.h_rowptr.data(), Kt.rowptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
-  CUT(cudaMemcpyAsync(h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
-  CUT(cudaStreamSynchronize(st));
+  cudaError_t e_back = cudaSuccess;
+  if (!planned_t) e_back = cudaMemcpyAsync(Kt.h_rowptr.data(), Kt.rowptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st);
+  if (e_back == cudaSuccess) e_back = cudaMemcpyAsync(h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, st);
+  if (e_back == cudaSuccess) e_back = cudaStreamSynchronize(st);
+  if (pin_rowptr) pinned_buf_put(pin_rowptr, pin_cap);
+  CUT(e_back);
   tmp_free();
 #undef TMP
 #undef CUT
@@ -1428,10 +1489,12 @@ static int ingest_host_csr(EngineT<T>* E, const void* h_rowptr, const void* h_co
   if (h_err[1]) return fail(PDLP_ERR_NOT_CANONICAL, "K is not a canonical CSR matrix (columns must be strictly increasing inside every row)");
   if (Kt.h_rowptr[(size_t)n] != nnz) return fail(PDLP_ERR_STATE, "transpose does not cover the matrix");
   tr.lap("wait: H2D + transpose");
-  int rc = upload_plan_and_pack<T>(E, K, PK);          // the device packs K while the host plans K^T
+  int rc = upload_plan_and_pack<T>(E, K, PK);          // the device packs K while the host plans K^T (if not done yet)
   if (rc) return rc;
-  HostSell PT = plan_csr<T>(E, Kt);
-  tr.lap("plan K^T (host, overlapped)");
+  if (!planned_t) {
+    PT = plan_csr<T>(E, Kt);
+    tr.lap("plan K^T (host, overlapped)");
+  }
   rc = upload_plan_and_pack<T>(E, Kt, PT);
   if (rc) return rc;
   CU(cudaStreamSynchronize(st));                        // PK, PT go out of scope
