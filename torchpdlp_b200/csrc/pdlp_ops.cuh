@@ -278,11 +278,31 @@ struct DualOp {
   const double* dx2_partials = nullptr;
   int dx2_blocks = 0;
   double dx2_tot = 0.0;
-  __device__ void pre_finalize() {
+  double dxv[5];
+  // loads issued before the kernel's own partial sums are read (one round trip for everything the finalize needs):
+  // the first 160 partial ||dx||^2 and the two cache lines of Scalars that hold the step state
+  __device__ void pre_finalize_issue() {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)S + 128));
     if (dx2_partials) {
-      double t[1];
-      grid_totals<1>(dx2_partials, MAX_RED, dx2_blocks, t);
-      dx2_tot = t[0];
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int b = lane + 32 * j;
+        dxv[j] = b < dx2_blocks ? __ldcg(dx2_partials + (size_t)b * MAX_RED) : 0.0;
+      }
+    }
+  }
+  __device__ void pre_finalize() {          // grid_totals' order: lane-strided sums from +0.0, then the xor tree
+    if (dx2_partials) {
+      const int lane = threadIdx.x & 31;
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) t += dxv[j];
+      for (int b = lane + 160; b < dx2_blocks; b += 32) t += __ldcg(dx2_partials + (size_t)b * MAX_RED);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += shfl_xor_t(t, o);
+      dx2_tot = t;
     }
   }
   __device__ bool begin() {
@@ -381,6 +401,9 @@ struct DualWindowOp {
     if constexpr (LAST) d.row_finish(i, k.in, a, red);
     else part[i] = Pair<T>{a[0], a[1]};
   }
+  __device__ void pre_finalize_issue() {
+    if constexpr (LAST) d.pre_finalize_issue();
+  }
   __device__ void pre_finalize() {
     if constexpr (LAST) d.pre_finalize();
   }
@@ -439,6 +462,9 @@ struct DualBarOp {
     } else {
       part[i] = u;
     }
+  }
+  __device__ void pre_finalize_issue() {
+    if constexpr (LAST) d.pre_finalize_issue();
   }
   __device__ void pre_finalize() {
     if constexpr (LAST) d.pre_finalize();

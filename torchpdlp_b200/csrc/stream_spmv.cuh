@@ -448,6 +448,31 @@ __device__ __forceinline__ void block_reduce(double (&red)[NRED > 0 ? NRED : 1],
 template <int NRED>
 __device__ __forceinline__ void grid_totals(const double* partials, int stride, int nblocks, double (&tot)[NRED > 0 ? NRED : 1]) {
   const int lane = threadIdx.x & 31;
+  constexpr int NB = 5;                    // 5 x 32 = 160 >= one CTA per SM on B200 (148)
+  if constexpr (NRED > 0 && NRED <= 8) {
+    if (nblocks <= 32 * NB) {
+      // every load issued before the first add: ONE L2 round trip for the whole table instead of one per dependent
+      // add (this runs in the tail of the kernel, on the critical path to the next one).  Same order of additions as
+      // the loop below (absent blocks contribute +0.0, which leaves a sum that started at +0.0 unchanged).
+      double v[NRED][NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int b = lane + 32 * j;
+#pragma unroll
+        for (int i = 0; i < NRED; ++i) v[i][j] = b < nblocks ? __ldcg(&partials[(size_t)b * stride + i]) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) t += v[i][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += shfl_xor_t(t, o);
+        tot[i] = t;
+      }
+      return;
+    }
+  }
   for (int i = 0; i < NRED; ++i) {
     double t = 0.0;
     for (int b = lane; b < nblocks; b += 32) t += __ldcg(&partials[(size_t)b * stride + i]);
@@ -462,11 +487,16 @@ __device__ __forceinline__ void grid_totals(const double* partials, int stride, 
 //                               next kernel's op adds them up itself (PrimalOp -> DualOp: ||dx||^2 is only needed by the
 //                               step rule, so K1's tail loses an atomic round trip, a re-read and a dependent store)
 //   void pre_finalize();        run by the whole first warp of the last CTA before lane 0 calls finalize
+//   void pre_finalize_issue();  same warp, BEFORE the partial sums are read: loads / prefetches the finalize will need,
+//                               so that they share the round trip of the partial sums
 template <class Op, class = void> struct op_has_defer : std::false_type {};
 template <class Op> struct op_has_defer<Op, std::void_t<decltype(std::declval<const Op&>().defer)>> : std::true_type {};
 template <class Op, class = void> struct op_has_pre_finalize : std::false_type {};
 template <class Op>
 struct op_has_pre_finalize<Op, std::void_t<decltype(std::declval<Op&>().pre_finalize())>> : std::true_type {};
+template <class Op, class = void> struct op_has_pre_finalize_issue : std::false_type {};
+template <class Op>
+struct op_has_pre_finalize_issue<Op, std::void_t<decltype(std::declval<Op&>().pre_finalize_issue())>> : std::true_type {};
 
 template <class Op>
 __global__ void __launch_bounds__(StreamCfg<typename Op::value_type>::NT, StreamCfg<typename Op::value_type>::MINB)
@@ -543,6 +573,7 @@ stream_kernel(const SellView<typename Op::value_type> A, Op op) {
     if (s_last && warp == 0) {
       __threadfence();
       double tot[NR];
+      if constexpr (op_has_pre_finalize_issue<Op>::value) op.pre_finalize_issue();
       grid_totals<NRED>(A.block_partials, MAX_RED, (int)gridDim.x, tot);
       if constexpr (op_has_pre_finalize<Op>::value) op.pre_finalize();
       if (lane == 0) {
