@@ -103,8 +103,8 @@ block_kernel(const SellView<T> Kt, const SellView<T> K, const BlockArgs<T> a) {
     // ---------------- every CTA: grid totals (fixed order) and the step rule on its own scalars ----------------
     if (warp == 0) {
       double t1[1], t2[2];
-      grid_totals<1>(a.partP + par * grid, 1, grid, t1);
-      grid_totals<2>(a.partD + par * grid * 2, 2, grid, t2);
+      grid_totals<1, false>(a.partP + par * grid, 1, grid, t1);
+      grid_totals<2, false>(a.partD + par * grid * 2, 2, grid, t2);
       if (lane == 0) {
         ls.dx2 = t1[0];
         ls.dy2 = t2[0];

@@ -1017,12 +1017,14 @@ __global__ void shard_primal_kernel(const double* kty, const T* c, const T* l, c
     s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && warp == 0) {           // one warp, batched loads (grid_totals): not a serial chain over the blocks
     __threadfence();
-    double a = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&partials[b]);
-    S->dx2 = a;
-    *ticket = 0u;
+    double a[1];
+    grid_totals<1>(partials, 1, (int)gridDim.x, a);
+    if (lane == 0) {
+      S->dx2 = a[0];
+      *ticket = 0u;
+    }
   }
 }
 
@@ -1119,23 +1121,23 @@ __device__ __forceinline__ void xchg_reduce_rule_primal(const Xchg& X, unsigned 
     s_int[0] = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_int[0] && threadIdx.x == 0) {
+  if (s_int[0] && warp == 0) {
     __threadfence();
-    Scalars& s = *S;
-    if (s_int[1]) {           // commit the rule every CTA evaluated (shard_rule_kernel's arithmetic)
-      s.k += 1;
-      s.dy2 = s_rule[2];
-      s.inter = s_rule[3];
-      commit_step(s, s_rule[4], s_rule[5]);
-      s.rule_pending = 0;
+    double a[1] = {0.0};
+    if (!s_stop) grid_totals<1>(partials, 1, (int)gridDim.x, a);      // one warp, batched loads
+    if (lane == 0) {
+      Scalars& s = *S;
+      if (s_int[1]) {           // commit the rule every CTA evaluated (shard_rule_kernel's arithmetic)
+        s.k += 1;
+        s.dy2 = s_rule[2];
+        s.inter = s_rule[3];
+        commit_step(s, s_rule[4], s_rule[5]);
+        s.rule_pending = 0;
+      }
+      if (!s_stop) s.dx2 = a[0];
+      s.xchg_seq = (unsigned long long)seq + 1;
+      *ticket = 0u;
     }
-    if (!s_stop) {
-      double a = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(&partials[b]);
-      s.dx2 = a;
-    }
-    s.xchg_seq = (unsigned long long)seq + 1;
-    *ticket = 0u;
   }
 }
 
@@ -1281,20 +1283,21 @@ __global__ void shard_kkt_cols_kernel(const double* kty3, const Quad<T>* X4, con
     s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && (threadIdx.x >> 5) == 0) {
     __threadfence();
-    for (int v = 0; v < 3; ++v) {
-      double t[5] = {0, 0, 0, 0, 0};
-      for (int b = 0; b < (int)gridDim.x; ++b)
-        for (int i = 0; i < 5; ++i) t[i] += __ldcg(&partials[(size_t)b * 16 + 5 * v + i]);
-      S->sums[v][S_DR2] = t[0];
-      S->sums[v][S_CTX] = t[1];
-      S->sums[v][S_LPOS] = t[2];
-      S->sums[v][S_UNEG] = t[3];
-      S->sums[v][S_DR2U] = t[4];
+    double t[15];
+    grid_totals<15>(partials, 16, (int)gridDim.x, t);       // one warp, batched loads
+    if ((threadIdx.x & 31) == 0) {
+      for (int v = 0; v < 3; ++v) {
+        S->sums[v][S_DR2] = t[5 * v + 0];
+        S->sums[v][S_CTX] = t[5 * v + 1];
+        S->sums[v][S_LPOS] = t[5 * v + 2];
+        S->sums[v][S_UNEG] = t[5 * v + 3];
+        S->sums[v][S_DR2U] = t[5 * v + 4];
+      }
+      S->w_pending = 0.0;
+      *ticket = 0u;
     }
-    S->w_pending = 0.0;
-    *ticket = 0u;
   }
 }
 

@@ -444,41 +444,56 @@ __device__ __forceinline__ void block_reduce(double (&red)[NRED > 0 ? NRED : 1],
   }
 }
 
-// per-CTA values of every CTA -> grid totals, by one warp, fixed order (lane-strided sums, then xor tree)
-template <int NRED>
+// per-CTA values of every CTA -> grid totals, by one warp, fixed order: lane l adds blocks l, l + 32, l + 64, ... from
+// +0.0, then the xor tree.  The loads are issued in batches of up to 8 sums x 5 blocks per lane before the first add --
+// ONE L2 round trip per batch instead of one per dependent add (this runs in the tail of a kernel, on the critical
+// path to the next one); an absent block contributes +0.0, which leaves a sum that started at +0.0 unchanged, so the
+// result equals the plain loop's bit for bit.
+// (BATCH = false: the plain loop, for callers that have no registers to spare -- the persistent block kernel)
+template <int NRED, bool BATCH = true>
 __device__ __forceinline__ void grid_totals(const double* partials, int stride, int nblocks, double (&tot)[NRED > 0 ? NRED : 1]) {
   const int lane = threadIdx.x & 31;
+  if constexpr (!BATCH) {
+    for (int i = 0; i < NRED; ++i) {
+      double t = 0.0;
+      for (int b = lane; b < nblocks; b += 32) t += __ldcg(&partials[(size_t)b * stride + i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += shfl_xor_t(t, o);
+      tot[i] = t;
+    }
+    return;
+  }
   constexpr int NB = 5;                    // 5 x 32 = 160 >= one CTA per SM on B200 (148)
-  if constexpr (NRED > 0 && NRED <= 8) {
-    if (nblocks <= 32 * NB) {
-      // every load issued before the first add: ONE L2 round trip for the whole table instead of one per dependent
-      // add (this runs in the tail of the kernel, on the critical path to the next one).  Same order of additions as
-      // the loop below (absent blocks contribute +0.0, which leaves a sum that started at +0.0 unchanged).
-      double v[NRED][NB];
+  constexpr int CH = NRED < 8 ? (NRED > 0 ? NRED : 1) : 8;
+#pragma unroll
+  for (int i0 = 0; i0 < NRED; i0 += CH) {
+    double t[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) t[i] = 0.0;
+    for (int c0 = 0; c0 < nblocks; c0 += 32 * NB) {
+      double v[CH][NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const int b = lane + 32 * j;
+        const int b = c0 + lane + 32 * j;
 #pragma unroll
-        for (int i = 0; i < NRED; ++i) v[i][j] = b < nblocks ? __ldcg(&partials[(size_t)b * stride + i]) : 0.0;
+        for (int i = 0; i < CH; ++i)
+          v[i][j] = (i0 + i < NRED && b < nblocks) ? __ldcg(&partials[(size_t)b * stride + i0 + i]) : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < NRED; ++i) {
-        double t = 0.0;
+      for (int i = 0; i < CH; ++i) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) t += v[i][j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += shfl_xor_t(t, o);
-        tot[i] = t;
+        for (int j = 0; j < NB; ++j) t[i] += v[i][j];
       }
-      return;
     }
-  }
-  for (int i = 0; i < NRED; ++i) {
-    double t = 0.0;
-    for (int b = lane; b < nblocks; b += 32) t += __ldcg(&partials[(size_t)b * stride + i]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += shfl_xor_t(t, o);
-    tot[i] = t;
+    for (int i = 0; i < CH; ++i) {
+      if (i0 + i < NRED) {
+        double r = t[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += shfl_xor_t(r, o);
+        tot[i0 + i] = r;
+      }
+    }
   }
 }
 
