@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p variants
 build() {
   name=$1; shift
-  nvcc -shared -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "$@" \
+  nvcc -shared -Xcompiler -fPIC -Xcompiler -pthread -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 "$@" \
     -Xptxas -v -o variants/lib_$name.so torchpdlp_b200/csrc/pdlp_b200.cu 2> variants/$name.ptxas.log
   echo "$name: built"
 }
