@@ -469,3 +469,50 @@ def test_in_loop_kernel_timing(cfg1):
         a.time_kernels_in_loop(4)
     a.close()
     b.close()
+
+
+def test_dense_xbar_kernels_track_the_pair_kernels(cfg1, monkeypatch):
+    """DualBarOp against DualOp at the kernel level: K2 gathers the dense xbar vector written by K1 and takes K dx from
+    the recursion v' = v + (K xbar - v) / (1 + theta) on v = K x.  One iteration: the dual update is bit-identical
+    (K xbar is formed by the same operations) and so is dy^T K dx (v = 0).  40 adaptive iterations: the step size -- the
+    only consumer of K dx -- and the iterates agree to 1e-10.  (Not longer: unrestarted adaptive iterations amplify
+    rounding by ~10^11 in 200 steps -- the oracle's scipy and torch backends, which differ in summation order only, are
+    2.5e-5 apart in eta by then -- so long runs are compared through whole solves, tests/test_gpu_solve.py.)  v is
+    rebuilt on the device after a restart and after set_iterate: the agreement holds across both."""
+    monkeypatch.setenv("PDLP_XBAR", "0")
+    a = make_engine(cfg1)
+    monkeypatch.setenv("PDLP_XBAR", "1")
+    b = make_engine(cfg1)
+    rel = lambda u, v: abs(u - v) / max(abs(v), 1e-300)
+    # dy^T K dx is a sum with cancellation: compare on the scale of ||dy|| ||dx|| ||K|| (||K|| < 20 here), not its own
+    close_inter = lambda sb, sa: abs(sb.inter - sa.inter) <= 1e-8 * (20.0 * (sa.dx2 * sa.dy2) ** 0.5 + abs(sa.inter))
+
+    def same(tol):
+        sa, sb = a.state(), b.state()
+        assert sa.k == sb.k and rel(sb.eta, sa.eta) < tol and close_inter(sb, sa), (sa.k, sa.eta, sb.eta, sa.inter, sb.inter)
+        for u, v in zip(a.get_iterate(), b.get_iterate()):
+            assert float((u - v).abs().max()) <= tol * max(1.0, float(u.abs().max()))
+
+    for e in (a, b):
+        e.set_iterate(None, None)
+        e.set_step(0.05, 1.0, 1.0, adaptive=True)
+        e.iterate(1, use_graph=False)
+    sa, sb = a.state(), b.state()
+    assert torch.equal(a.get_iterate()[1], b.get_iterate()[1]) and torch.equal(a.get_iterate()[0], b.get_iterate()[0])
+    assert sa.dy2 == sb.dy2 and sa.dx2 == sb.dx2 and rel(sb.inter, sa.inter) < 1e-12
+    for e in (a, b):
+        e.iterate(39, save_previous=True, use_graph=True)
+    same(1e-10)
+    ca, cb = a.restart_check(True), b.restart_check(True)           # forced restart: v = K x recomputed on the device
+    assert (ca.kind, ca.use_average) == (cb.kind, cb.use_average) and rel(cb.kkt_current, ca.kkt_current) < 1e-9
+    for e in (a, b):
+        e.iterate(40, use_graph=True)
+    same(1e-8)
+    x0, y0 = a.get_iterate()
+    for e in (a, b):                                                 # non-zero start through set_iterate
+        e.set_iterate(x0, y0)
+        e.set_step(0.05, 1.0, 1.0, adaptive=True)
+        e.iterate(40, use_graph=True)
+    same(1e-10)
+    a.close()
+    b.close()

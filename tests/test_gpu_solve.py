@@ -349,6 +349,8 @@ def test_cfg1_solve_on_dense_xbar(adaptive, pw, window_mb, cfg1, monkeypatch):
         assert (k2, j2) == (gold_r["k"], gold_r["j"]) and rel(obj2, gold_r["obj"]) < 1e-9
     x3, obj3, k3, n3, j3, status3, *_ = solve(cfg1, adaptive=adaptive, primal_weight=pw, verbose=True)
     assert (status3, n3) == (status, n) and abs(k3 - k) <= (40 if adaptive else 0) and rel(obj3, obj) < (ADAPTIVE_REL if adaptive else 1e-12)
+    x4, obj4, k4, n4, j4, status4, *_ = solve(cfg1, adaptive=adaptive, primal_weight=pw, x_init=x, y_init=info["y"])
+    assert status4 == "Solved" and k4 == 40 and rel(obj4, obj) < 1e-4          # terminates at the first restart test
 
 
 def test_cfg2_ruiz_full_size_against_oracle():
