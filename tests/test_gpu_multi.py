@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, exchange, adaptive, pw, which, out):
+def _worker(rank, world, port, exchange, adaptive, pw, which, out, ruiz=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -37,7 +37,12 @@ def _worker(rank, world, port, exchange, adaptive, pw, which, out):
     mi = min(max(lp.m_ineq - r0, 0), r1 - r0)
     Kb = lp.K[r0:r1].tocsr()
     Kb.sort_indices()
-    solver = build_rank_engine(Kb, mi, lp.c, lp.q[r0:r1], lp.l, lp.u, device=dev, exchange=exchange)
+    if ruiz:
+        from torchpdlp_b200.sharded import ruiz_precondition_sharded
+        Ks, c, q, l, u, d_row, d_col, _ = ruiz_precondition_sharded(Kb, lp.c, lp.q[r0:r1], lp.l, lp.u)
+        solver = build_rank_engine(Ks, mi, c, q, l, u, device=dev, exchange=exchange, scaling=(d_row, d_col))
+    else:
+        solver = build_rank_engine(Kb, mi, lp.c, lp.q[r0:r1], lp.l, lp.u, device=dev, exchange=exchange)
     torch.manual_seed(0)
     x, y, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=pw)
     lo, hi = x.clone(), x.clone()
@@ -51,12 +56,12 @@ def _worker(rank, world, port, exchange, adaptive, pw, which, out):
     dist.destroy_process_group()
 
 
-def run_world(exchange, adaptive, pw, which="cfg1", world=2):
+def run_world(exchange, adaptive, pw, which="cfg1", world=2, ruiz=False):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, adaptive, pw, which, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, adaptive, pw, which, out, ruiz)) for r in range(world)]
     for p in procs:
         p.start()
     import queue
@@ -130,6 +135,20 @@ def test_two_gpu_solve_on_dense_xbar(exchange, window_mb, adaptive, pw, monkeypa
         assert abs(res["k"] - gold["k"]) <= 40 and rel < 1e-6, (res["k"], gold["k"], rel)
     else:
         assert (res["k"], res["j"]) == (gold["k"], gold["j"]) and rel < 1e-9
+
+
+@needs_two
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_gpu_solve_with_ruiz(exchange):
+    """Ruiz on two ranks (column maxima by all_reduce(MAX) over NCCL, on the GPUs) + the scaled solve that terminates
+    on the original problem's residuals, against the executed reference's precondition=True run (fixed step)."""
+    with open(os.path.join(GOLD, "cfg1_reference.json")) as f:
+        runs = json.load(f)["runs"]
+    gold = [r for r in runs if r["options"] == dict(ruiz=True, fishnet=False, adaptive=False, primal_weight=False)][0]["reference"]
+    res = run_world(exchange, False, False, ruiz=True)
+    assert res["same_x"] and res["status"] == gold["status"]
+    assert (res["k"], res["n"], res["j"]) == (gold["k"], gold["n"], gold["j"])
+    assert abs(res["obj"] - gold["obj"]) <= 1e-9 * abs(gold["obj"])
 
 
 @needs_two

@@ -228,6 +228,34 @@ def test_sharded_entry_points_single_rank(adaptive, pw, cfg1):
         assert (k, j) == (gold["k"], gold["j"]) and rel(obj, gold["obj"]) < 1e-9
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+@pytest.mark.parametrize("adaptive,pw", [(False, False), (True, True)])
+def test_sharded_ruiz_single_rank(adaptive, pw, exchange, cfg1):
+    """Ruiz on the row-partitioned engine (sharded.ruiz_precondition_sharded -> build_rank_engine(scaling=...)): the
+    scaled problem is solved, the restart tests terminate on the residuals of the original one.  World size 1 against
+    the executed reference's precondition=True runs: fixed step k / n / j equal, adaptive within the band; D_col x is
+    feasible for the ORIGINAL problem to the tolerance.  (Two ranks: tests/test_gpu_multi.py; the scaling itself on two
+    ranks, bit for bit against the single-process one: tests/test_sharded_gloo.py.)"""
+    from torchpdlp_b200.sharded import build_rank_engine, ruiz_precondition_sharded
+    torch.set_default_dtype(torch.float64)
+    gold = [r for r in CFG1_RUNS if r["options"] == dict(ruiz=True, fishnet=False, adaptive=adaptive, primal_weight=pw)][0]["reference"]
+    Ks, c, q, l, u, d_row, d_col, rounds = ruiz_precondition_sharded(cfg1.K, cfg1.c, cfg1.q, cfg1.l, cfg1.u)
+    solver = build_rank_engine(Ks, cfg1.m_ineq, c, q, l, u, exchange=exchange, scaling=(d_row, d_col))
+    torch.manual_seed(0)
+    x, y, obj, k, n, j, status, secs, sigma = solver.solve(adaptive=adaptive, primal_update=pw)
+    solver.close()
+    assert status == gold["status"] and n == gold["n"]
+    if adaptive:
+        assert abs(k - gold["k"]) <= 40 and rel(obj, gold["obj"]) < 2e-6
+    else:
+        assert (k, j) == (gold["k"], gold["j"]) and rel(obj, gold["obj"]) < 1e-9
+    xv = x.cpu().numpy().reshape(-1) * d_col
+    r = cfg1.K @ xv - cfg1.q
+    viol = np.concatenate([np.minimum(r[:cfg1.m_ineq], 0.0), r[cfg1.m_ineq:]])
+    assert np.linalg.norm(viol) <= 1e-4 * (1 + np.linalg.norm(cfg1.q)) * (1 + 1e-9)
+    assert rel(float(cfg1.c @ xv), obj) < 1e-9
+
+
 def test_infeasibility_verdicts_match_executed_reference():
     """Small LPs from the golden file: the reference's certificate heuristic (enhancements.py:106-161), incl. the
     LPs it mislabels, reproduced verdict for verdict with the tests fused into the iteration kernels."""

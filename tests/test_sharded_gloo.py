@@ -136,3 +136,54 @@ def test_partition_rows_balances_nnz():
         assert cuts[0] == 0 and cuts[-1] == lp.m and np.all(np.diff(cuts) > 0)
         nnz = np.diff(lp.K.indptr[cuts])
         assert nnz.max() <= 1.35 * nnz.mean()
+
+
+def _ruiz_worker(rank, world, port, which, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_default_dtype(torch.float64)
+    from torchpdlp_b200 import synthetic
+    from torchpdlp_b200.sharded import partition_rows, ruiz_precondition_sharded
+    lp = synthetic.feasible_lp() if which == "cfg1" else synthetic.mixed_bounds_lp()
+    cuts = partition_rows(lp.K.indptr, world)
+    r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+    Ks, c, q, l, u, d_row, d_col, rounds = ruiz_precondition_sharded(lp.K[r0:r1], lp.c, lp.q[r0:r1], lp.l, lp.u)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(dict(d_row=d_row, q=q, vals=Ks.data, d_col=d_col, c=c, l=l, u=u, rounds=rounds), parts, dst=0)
+    if rank == 0:
+        out.put(parts)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("which", ["cfg1", "mixed_bounds"])
+def test_two_rank_ruiz_equals_the_single_process_scaling(which):
+    """ruiz_precondition_sharded on two row blocks (column maxima and the stopping test meet in one all_reduce(MAX)
+    per round) against the oracle's Ruiz on the whole matrix -- which the executed reference pins
+    (tests/golden/cfg1_functions.npz): same number of rounds, D_row / D_col / scaled values / c, q, l, u bit for bit
+    (max, sqrt and division are exact operations; nothing depends on a summation order); infinite bounds stay infinite."""
+    from oracle import pdlp_oracle as orc
+    from torchpdlp_b200 import synthetic
+    torch.set_default_dtype(torch.float64)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ruiz_worker, args=(r, 2, port, which, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lp = synthetic.feasible_lp() if which == "cfg1" else synthetic.mixed_bounds_lp()
+    t = lambda v: torch.from_numpy(np.asarray(v, dtype=np.float64))
+    op = orc.Operator(lp.K, backend="scipy")
+    sop, c_s, q_s, l_s, u_s, sc = orc.precondition(op, t(lp.c), t(lp.q), t(lp.l), t(lp.u))
+    assert parts[0]["rounds"] == parts[1]["rounds"] == sc.rounds
+    for key in ("d_col", "c", "l", "u"):                       # replicated: both ranks hold the same bits
+        assert np.array_equal(parts[0][key], parts[1][key])
+    assert np.array_equal(parts[0]["d_col"], sc.D_col.numpy()) and np.array_equal(parts[0]["c"], c_s.numpy())
+    assert np.array_equal(parts[0]["l"], l_s.numpy()) and np.array_equal(parts[0]["u"], u_s.numpy())
+    assert np.array_equal(np.concatenate([p["d_row"] for p in parts]), sc.D_row.numpy())
+    assert np.array_equal(np.concatenate([p["q"] for p in parts]), q_s.numpy())
+    rows, cols, vals = sop.triplets()                           # row-major, like the concatenated CSR blocks
+    assert np.array_equal(np.concatenate([p["vals"] for p in parts]), vals.numpy())

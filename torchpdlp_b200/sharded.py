@@ -41,6 +41,60 @@ def partition_rows(indptr: np.ndarray, parts: int, row_cost: float = 6.0) -> np.
     return np.concatenate([[0], cuts, [m]]).astype(np.int64)
 
 
+def ruiz_precondition_sharded(K_local, c, q_local, l, u, group=None, max_iter=20, eps=1e-6, device=None):
+    """Ruiz equilibration (PDLP/enhancements.py:4-71) of a ROW-PARTITIONED problem: this rank holds the rows K_local
+    (scipy CSR, canonical) with q_local; c, l, u are replicated.  Per round, as in the reference: rows divided by
+    sqrt(row inf-norm) -- local --, then columns by sqrt(col inf-norm) of the row-scaled matrix -- the per-rank column
+    maxima meet in ONE all_reduce(MAX) of n doubles --, norms below eps count as 1; the loop ends when
+    max |1 - row_norm| < eps over ALL ranks (the reference tests the row norms twice and never the column norms,
+    :60-61; the rank-local maxima ride in the last slot of the same all_reduce, so the decision is collective and costs
+    no collective of its own).  max is associative and commutative, sqrt and division are correctly rounded: every rank
+    gets the bits a single process gets on the whole matrix.
+
+    Runs on ``device`` (default: the GPU under NCCL, the CPU under gloo / without a process group).  Returns
+    ``(K_s_local, c_s, q_s_local, l_s, u_s, D_row_local, D_col, rounds)`` -- scipy CSR + numpy arrays, ready for
+    :func:`build_rank_engine` (``scaling=(D_row_local, D_col)``); the minimizer of the scaled problem times D_col is the
+    minimizer of the original one (primal_dual_hybrid_gradient.py:161)."""
+    import scipy.sparse as sp
+    K_local = sp.csr_matrix(K_local)
+    m_loc, n = K_local.shape
+    use_dist = dist.is_initialized() and dist.get_world_size(group) > 1
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if (use_dist and dist.get_backend(group) == "nccl") \
+            else torch.device("cpu")
+    f64 = dict(dtype=torch.float64, device=device)
+    vals = torch.as_tensor(np.asarray(K_local.data, dtype=np.float64)).to(device).clone()
+    cols = torch.as_tensor(K_local.indices.astype(np.int64)).to(device)
+    lengths = torch.as_tensor(np.diff(K_local.indptr).astype(np.int64)).to(device)
+    D_row = torch.ones(m_loc, **f64)
+    D_col = torch.ones(n, **f64)
+    rounds = 0
+    for _ in range(int(max_iter)):
+        rounds += 1
+        rn = torch.segment_reduce(vals.abs(), "max", lengths=lengths, unsafe=True) if vals.numel() else torch.zeros(m_loc, **f64)
+        rn = torch.where(lengths > 0, rn, torch.zeros_like(rn)).sqrt()           # an empty row has norm 0 -> 1 below
+        rn = torch.where(rn < eps, torch.ones_like(rn), rn)
+        D_row /= rn
+        vals /= torch.repeat_interleave(rn, lengths)
+        buf = torch.zeros(n + 1, **f64)                                          # [column maxima | max |1 - row norm|]
+        buf[:n].scatter_reduce_(0, cols, vals.abs(), "amax", include_self=True)
+        buf[n] = torch.max(torch.abs(1.0 - rn)) if m_loc else 0.0
+        if use_dist:
+            dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
+        cn = buf[:n].sqrt()
+        cn = torch.where(cn < eps, torch.ones_like(cn), cn)
+        D_col /= cn
+        vals /= cn[cols]
+        if float(buf[n]) < eps:
+            break
+    to_np = lambda t: t.detach().cpu().numpy()
+    d_row, d_col = to_np(D_row), to_np(D_col)
+    K_s = sp.csr_matrix((to_np(vals), K_local.indices.copy(), K_local.indptr.copy()), shape=K_local.shape)
+    as_np = lambda v: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float64)).reshape(-1)
+    c, q_local, l, u = as_np(c), as_np(q_local), as_np(l), as_np(u)
+    return K_s, c * d_col, q_local * d_row, l / d_col, u / d_col, d_row, d_col, rounds
+
+
 class GpuShardPrims:
     """The C-ABI calls of one rank (a thin veneer over :class:`Engine`)."""
 
@@ -378,8 +432,12 @@ class ShardedSolver:
         return x, y_local, prim_obj, k, n, j, status, time.time() - t0, sigma
 
 
-def build_rank_engine(K_local, m_ineq_local: int, c, q_local, l, u, device=None, exchange="nccl"):
-    """Engine on this rank's rows + the sharded driver."""
+def build_rank_engine(K_local, m_ineq_local: int, c, q_local, l, u, device=None, exchange="nccl", scaling=None):
+    """Engine on this rank's rows + the sharded driver.  ``scaling = (D_row_local, D_col)``: the problem passed in is
+    the Ruiz-scaled one (:func:`ruiz_precondition_sharded`); the restart tests then terminate on the residuals of the
+    ORIGINAL problem, as the reference does with ``precondition=True`` (primal_dual_hybrid_gradient.py:153-177)."""
     from .engine import Engine
     eng = Engine(K_local, m_ineq_local, c, q_local, l, u, device=device, dtype=torch.float64)
+    if scaling is not None:
+        eng.set_scaling(scaling[0], scaling[1])
     return ShardedSolver(GpuShardPrims(eng), exchange=exchange)
