@@ -194,6 +194,7 @@ def pdlp_algorithm(K, m_ineq, c, q, l, u, device, max_kkt=100_000, tol=1e-4, ver
     lap("solve")
     x, y = engine.get_iterate()
     torch.cuda.synchronize(engine.device)
+    lap("get_iterate")
     total = time.time() - t_start + time_used
     if trace_t is not None:
         prev = t_start
